@@ -1,0 +1,162 @@
+/* michigan_b200 — C ABI of libmichigan_sm100.so (hand-written CUDA for sm_100a).
+ *
+ * This is the drop-in boundary for the MichiGAN data-parallel hot path.  The reference has no
+ * native code: every entry point below replaces a group of PyTorch ops that the reference calls
+ * from Python (file:line cited per function, relative to the reference repo root).  The reference-
+ * side binding is a ctypes stub (see INTEGRATION.md and michigan_b200/_lib.py).
+ *
+ * Conventions (all functions):
+ *   - plain device pointers + explicit sizes, fp32 data, activations NHWC ([N,H,W,C], C fastest);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the device, nothing
+ *     allocates device memory; work is enqueued on `stream`;
+ *   - return 0 on success, <0 for a rejected argument, >0 = cudaError_t; mg_last_error() gives the
+ *     message of the calling thread's last failure;
+ *   - re-entrant across host threads and devices (no global mutable state besides a per-thread
+ *     error string and a one-time driver entry-point lookup).
+ */
+#ifndef MICHIGAN_B200_H
+#define MICHIGAN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+int mg_version(void);
+const char* mg_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+long long mg_launch_count(void);
+
+/* activation codes */
+#define MG_ACT_NONE 0
+#define MG_ACT_RELU 1
+#define MG_ACT_LRELU 2 /* LeakyReLU(0.2): architecture.py:84-85, discriminator.py:85,93 */
+#define MG_ACT_TANH 3
+
+/* epilogue kinds of the implicit-GEMM convolution */
+#define MG_EPI_BIAS 0  /* y = act((acc*pscale + bias + residual) ...) (+ blend)            */
+#define MG_EPI_SPADE 1 /* y = act(xhat*(1+gamma)+beta), gamma|beta = the two halves of acc */
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TF32 operands, fp32 accumulate in TMEM).
+ * Replaces nn.Conv2d / F.conv2d at: normalization.py:97-98,112-113 (mlp_gamma/mlp_beta, fused with
+ * the modulation of normalization.py:116 and the LeakyReLU of architecture.py:84-85),
+ * architecture.py:31-34,70-71,79 (conv_0/conv_1/conv_s), MaskGAN_networks.py:162-168 (ConvBlock
+ * convs of BackgroundEncode2), partialconv2d.py:69 (PartialConv2d), discriminator.py:84-96.
+ *
+ *   in      : [N,H,W,Cin] fp32, Cin % 32 == 0 (operands are read as TF32: producers round with RNA)
+ *   wpack   : [CoutG, KH*KW*Cin] fp32, K index = (kh*KW+kw)*Cin + ci  (see mg_pack_weight*)
+ *   out     : [N,OH,OW,Cout]
+ * MG_EPI_BIAS : CoutG == Cout.  y = acc*pscale[pix] + bias[c] + res[n,oh>>res_shift,ow>>res_shift,c];
+ *               y = act(y); if (bf) y = bf[pix,c]*(1-hair[n,oh*ms,ow*ms]) + y*(1-back[n,oh*ms,ow*ms]);
+ *               y *= pmul[pix].   (null pointers skip a term)
+ * MG_EPI_SPADE: CoutG == 2*Cout, packed per N-tile as [gamma(BN/2) | beta(BN/2)].
+ *               xh = x[n,oh>>x_shift,ow>>x_shift,c]*nscale[c] + nshift[c];
+ *               y = act(xh*(gbias1[c] + acc_gamma) + (bbias[c] + acc_beta)),  gbias1 = 1 + bias_gamma.
+ */
+typedef struct mg_igemm_args {
+    const float* in;
+    const float* wpack;
+    float* out;
+    int32_t N, H, W, Cin;
+    int32_t OH, OW, Cout;
+    int32_t KH, KW, stride, pad;
+    int32_t BN;        /* GEMM N tile (32..256, multiple of 32); 0 = choose */
+    int32_t epi, act, round_out;
+    const float* bias;
+    const float* res;
+    int32_t res_shift;
+    const float* pscale;
+    const float* pmul;
+    const float* bf;
+    const float* hair;
+    const float* back;
+    int32_t mask_stride, MH, MW; /* hair/back are [N,MH,MW] full-resolution masks */
+    const float* x;
+    int32_t x_shift;
+    const float* nscale;
+    const float* nshift;
+    const float* gbias1;
+    const float* bbias;
+    int32_t max_ctas; /* 0 = one CTA per SM */
+} mg_igemm_args;
+int mg_conv_igemm(const mg_igemm_args* a, void* stream);
+
+/* OIHW -> [O][kh][kw][I] repack, multiplied by *inv_sigma (device scalar, may be null), rounded to
+ * TF32 (RNA).  Spectral-norm scaling W/sigma: torch SpectralNorm.compute_weight as applied at
+ * architecture.py:38-42, normalization.py:28-29. */
+int mg_pack_weight(const float* w_oihw, float* wpack, int O, int I, int KH, int KW,
+                   const float* inv_sigma, int round_tf32, void* stream);
+/* gamma/beta pair -> one [2C][9*128] operand, interleaved per N-tile of BN rows:
+ * rows [t*BN, t*BN+BN/2) = gamma channels t*BN/2.., rows [t*BN+BN/2, (t+1)*BN) = beta channels. */
+int mg_pack_weight_gb(const float* wg_oihw, const float* wb_oihw, float* wpack, int C, int I, int KH,
+                      int KW, int BN, void* stream);
+
+/* Thin direct convolutions on CUDA cores (exact fp32): layers whose Cin is 3/4/7.
+ * mode 0: zero padding; mode 1: reflection padding (MaskGAN_networks.py:120-121);
+ * in [N,H,W,CinP] with CinP in {4,8} (channels zero-padded), w [KH*KW][CinP][Cout], Cout%32==0.
+ * seg_resize > 0: `in` is the full-resolution [N,H*seg_resize,W*seg_resize,4] segmap and the conv
+ * reads its legacy-nearest downsample (normalization.py:110) without materialising it. */
+typedef struct mg_thin_args {
+    const float* in;
+    const float* w;
+    const float* bias;
+    float* out;
+    int32_t N, H, W, CinP, OH, OW, Cout, KH, KW, stride, pad, pad_mode, seg_resize;
+    int32_t act, round_out;
+    const float* pscale;
+    const float* pmul;
+} mg_thin_args;
+int mg_conv_thin(const mg_thin_args* a, void* stream);
+int mg_pack_weight_thin(const float* w_oihw, float* wt, int O, int I, int CinP, int KH, int KW, void* stream);
+
+/* conv_img: tanh(conv3x3(lrelu(x))) 64->3, NHWC in, NCHW out (generator.py:227-228). */
+int mg_conv_img(const float* x, const float* w_oihw, const float* bias, float* out_nchw, int N, int H, int W,
+                int Cin, int Cout, int act_in, int act_out, void* stream);
+/* final PatchGAN logits: Cin->1, k4 s1 p2 (discriminator.py:96); out [N,OH,OW]. */
+int mg_conv_to1(const float* x, const float* w_oihw, const float* bias, float* out, int N, int H, int W, int Cin,
+                int KH, int KW, int pad, void* stream);
+
+/* Param-free batch-norm statistics (sync_batchnorm/batchnorm.py:63-93,128-145; F.batch_norm path
+ * batchnorm.py:65-68).  sums: [2*C] doubles (sum, sum of squares), accumulated (caller zeroes).   */
+int mg_bn_stats(const float* x, long long P, int C, double* sums, void* stream);
+/* mean/var from (all-reduced) sums over `count` values -> nscale = rstd, nshift = -mean*rstd;
+ * running_mean/var momentum update with unbiased variance of `count_unbiased` samples
+ * (pass null to skip).  clamp_mode 0: 1/sqrt(var+eps) (batchnorm.py:65-68); 1: clamp(var,eps)^-0.5
+ * (batchnorm.py:145). */
+int mg_bn_finalize(const double* sums, int C, double count, double count_unbiased, float eps, float momentum,
+                   int clamp_mode, float* nscale, float* nshift, float* running_mean, float* running_var,
+                   float* mean_out, float* var_out, void* stream);
+/* eval mode: nscale/nshift from running stats. */
+int mg_bn_from_running(const float* running_mean, const float* running_var, int C, float eps, float* nscale,
+                       float* nshift, void* stream);
+
+/* InstanceNorm2d(affine=False) + LeakyReLU (normalization.py:47-48,52; encoder.py:173-204):
+ * stats per (n,c) over HW (biased var, eps), then y = act((x-mean)*rstd) * pmul[pix]. */
+int mg_in_stats(const float* x, int N, long long HW, int C, double* sums /* [N][2][C] */, void* stream);
+/* ss: [N][2][C] float workspace that receives (rstd, -mean*rstd) */
+int mg_in_apply(const float* x, const double* sums, float* ss, float* y, int N, long long HW, int C, float eps, int act,
+                int round_out, const float* pmul, void* stream);
+
+/* Input preparation (generator.py:129-142; pix2pix_model.py:549-566).
+ * seg4 [N,H,W,4] = (tag0, tag1, sin(2th)*hair, cos(2th)*hair), th = orient/255*pi; orient_c==2 passes
+ * the two orientation channels through (--use_ig). */
+int mg_prep_seg(const float* tag_nchw, const float* orient_nchw, int orient_c, float* seg4, int N, int H, int W,
+                void* stream);
+/* D input [N,H,W,8] = (tag0, tag1, o0, o1, r, g, b, 0) from NHWC seg4 + NCHW image. */
+int mg_prep_dinput(const float* seg4, const float* img_nchw, float* out8, int N, int H, int W, void* stream);
+/* background-encoder input (encoder.py:321): img*back + noise*(1-back) -> [N,H,W,4]. */
+int mg_prep_bginput(const float* img_nchw, const float* noise_nchw, const float* back, float* out4, int N, int H,
+                    int W, void* stream);
+/* NCHW [N,C,H,W] -> NHWC with channel padding to CP. */
+int mg_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, int CP, void* stream);
+int mg_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, int CP, void* stream);
+/* max_pool2d(k, stride 1, pad k/2) on a 1-channel map (encoder.py:296,310-313); out = 1 - pool if invert. */
+int mg_maxpool_mask(const float* in, float* out, float* tmp, int N, int H, int W, int k, int invert, void* stream);
+/* avg_pool2d(k3,s2,p1,count_include_pad=False) on NHWC (discriminator.py:46-49). */
+int mg_avgpool3s2(const float* in, float* out, int N, int H, int W, int C, int OH, int OW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

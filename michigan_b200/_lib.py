@@ -1,0 +1,107 @@
+"""ctypes binding of libmichigan_sm100.so (C ABI declared in include/michigan_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an exception is
+raised.  The product path never routes through PyTorch eager or the CPU oracle.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmichigan_sm100.so")
+
+c_f32p = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
+
+
+class IgemmArgs(C.Structure):
+    _fields_ = [
+        ("inp", c_f32p), ("wpack", c_f32p), ("out", c_f32p),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("OH", C.c_int32), ("OW", C.c_int32), ("Cout", C.c_int32),
+        ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("BN", C.c_int32),
+        ("epi", C.c_int32), ("act", C.c_int32), ("round_out", C.c_int32),
+        ("bias", c_f32p), ("res", c_f32p), ("res_shift", C.c_int32),
+        ("pscale", c_f32p), ("pmul", c_f32p),
+        ("bf", c_f32p), ("hair", c_f32p), ("back", c_f32p),
+        ("mask_stride", C.c_int32), ("MH", C.c_int32), ("MW", C.c_int32),
+        ("x", c_f32p), ("x_shift", C.c_int32),
+        ("nscale", c_f32p), ("nshift", c_f32p), ("gbias1", c_f32p), ("bbias", c_f32p),
+        ("max_ctas", C.c_int32),
+    ]
+
+
+class ThinArgs(C.Structure):
+    _fields_ = [
+        ("inp", c_f32p), ("w", c_f32p), ("bias", c_f32p), ("out", c_f32p),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("CinP", C.c_int32),
+        ("OH", C.c_int32), ("OW", C.c_int32), ("Cout", C.c_int32),
+        ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("pad_mode", C.c_int32), ("seg_resize", C.c_int32),
+        ("act", C.c_int32), ("round_out", C.c_int32),
+        ("pscale", c_f32p), ("pmul", c_f32p),
+    ]
+
+
+_i, _ll, _f, _d, _p = C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_void_p
+
+# name -> argtypes (all return int unless noted); mirrors include/michigan_b200.h
+SIGNATURES = {
+    "mg_version": [],
+    "mg_last_error": [],
+    "mg_launch_count": [],
+    "mg_conv_igemm": [C.POINTER(IgemmArgs), _p],
+    "mg_pack_weight": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
+    "mg_pack_weight_gb": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_conv_thin": [C.POINTER(ThinArgs), _p],
+    "mg_pack_weight_thin": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_conv_img": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_conv_to1": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_bn_stats": [_p, _ll, _i, _p, _p],
+    "mg_bn_finalize": [_p, _i, _d, _d, _f, _f, _i, _p, _p, _p, _p, _p, _p, _p],
+    "mg_bn_from_running": [_p, _p, _i, _f, _p, _p, _p],
+    "mg_in_stats": [_p, _i, _ll, _i, _p, _p],
+    "mg_in_apply": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _i, _p, _p],
+    "mg_prep_seg": [_p, _p, _i, _p, _i, _i, _i, _p],
+    "mg_prep_dinput": [_p, _p, _p, _i, _i, _i, _p],
+    "mg_prep_bginput": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "mg_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+}
+
+_lib = None
+
+
+class MichiganNativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MichiganNativeError(
+            "libmichigan_sm100.so not found at %s - run `python -m michigan_b200.build` "
+            "(the CUDA extension is mandatory; there is no fallback path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.mg_last_error.restype = C.c_char_p
+    lib.mg_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mg_last_error().decode("utf-8", "replace")
+        raise MichiganNativeError("%s failed (status %d): %s" % (what or "libmichigan_sm100 call", rc, msg))
+
+
+def launch_count():
+    return int(load().mg_launch_count())

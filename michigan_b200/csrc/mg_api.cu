@@ -1,0 +1,67 @@
+// michigan_b200 — C-ABI glue: error strings, launch counter, driver entry points.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include "mg_internal.h"
+
+namespace mg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode_tensor_map(CUtensorMap* map, void* gaddr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const cuuint32_t* estrides, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(-100, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, gaddr, dims, strides, box, estrides,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(-101, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r,
+                         rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return 0;
+}
+
+}  // namespace mg
+
+extern "C" int mg_version(void) { return MG_ABI_VERSION; }
+extern "C" const char* mg_last_error(void) { return mg::g_err; }
+extern "C" long long mg_launch_count(void) { return mg::g_launches.load(); }

@@ -1,0 +1,405 @@
+// michigan_b200 — im2col-free implicit-GEMM convolution on tcgen05 (sm_100a).
+//
+//   D[pixels(128) x BN] += sum_{tap, cin-chunk} A_tap[pixels x 32] * W[BN x 32]^T
+//
+// * activations NHWC; one TMA 4-D box per (tap, 32-channel chunk): the box start is shifted by the
+//   tap offset and TMA's out-of-bounds zero fill implements the conv zero padding; strided convs
+//   use the tensor map's elementStrides (traversal stride) so no im2col / space-to-depth copy exists;
+// * weights pre-packed tap-major [CoutG][KH*KW*Cin] and loaded by a 2-D TMA box;
+// * both operands land in 128B-swizzled K-major smem tiles that tcgen05.mma (kind::tf32) reads
+//   directly; fp32 accumulators live in TMEM, double buffered so the epilogue of tile i overlaps
+//   the main loop of tile i+1;
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue;
+// * persistent CTAs (<= 1 per SM), static round-robin tile schedule with the N-tile index fastest
+//   so CTAs running concurrently share activation tiles through L2.
+//
+// Epilogues: bias/activation/residual/background-blend, and the fused SPADE modulation
+// (normalization.py:116 + architecture.py:84-85 of the reference).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include "mg_ptx.cuh"
+#include "mg_internal.h"
+
+namespace mg {
+
+constexpr int kNumEpiWarps = 8;
+constexpr int kThreads = 64 + kNumEpiWarps * 32;  // 320
+constexpr int kABytes = 128 * 128;                // 128 pixels x 32 fp32
+constexpr int kMaxStages = 8;
+
+struct IgemmParams {
+    int N, OH, OW, Cout;
+    int Cin, KH, KW, stride, pad;
+    int TW, TH, TN, tiles_w, tiles_h, tiles_n;
+    int BN, n_tiles, num_tiles, kchunks, stages;
+    uint32_t idesc, tmem_cols;
+    int epi, act, round_out;
+    float* out;
+    const float* bias;
+    const float* res;
+    int res_shift, RH, RW;
+    const float* pscale;
+    const float* pmul;
+    const float* bf;
+    const float* hair;
+    const float* back;
+    int mask_stride, MH, MW;
+    const float* x;
+    int x_shift, XH, XW;
+    const float* nscale;
+    const float* nshift;
+    const float* gbias1;
+    const float* bbias;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.2f * v;
+    if (act == 3) return tanhf(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const IgemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-align the operand ring (SWIZZLE_128B atoms are 1024 B).
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = kABytes + p.BN * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], kNumEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ksteps = p.KH * p.KW * p.kchunks;
+    const int m_tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            const uint32_t tx = kABytes + p.BN * 128;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int m = tile / p.n_tiles;
+                const int tw = m % p.tiles_w;
+                const int th = (m / p.tiles_w) % p.tiles_h;
+                const int tn = m / m_tiles_per_img;
+                const int iw0 = tw * p.TW * p.stride - p.pad;
+                const int ih0 = th * p.TH * p.stride - p.pad;
+                const int n0 = tn * p.TN;
+                for (int tap = 0; tap < p.KH * p.KW; ++tap) {
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&empty_bar[st], ph ^ 1);
+                        uint8_t* sa = smem + (size_t)st * stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[st], tx);
+                        tma_load_4d(sa, &tmA, &full_bar[st], kc * 32, iw0 + kw, ih0 + kh, n0);
+                        tma_load_2d(sa + kABytes, &tmB, &full_bar[st], tap * p.Cin + kc * 32, nt * p.BN);
+                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t aph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint64_t da = umma_desc_kmajor_sw128(sa);
+                    const uint64_t db = umma_desc_kmajor_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in 16 B units
+                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
+                                  (ks | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[st]);  // frees the smem stage when these MMAs retire
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+        const int half = ew >> 2;               // column half handled by this warp
+        const int r = quarter * 32 + lane;      // accumulator row == pixel within tile
+        const int wl = r % p.TW;
+        const int hl = (r / p.TW) % p.TH;
+        const int nl = r / (p.TW * p.TH);
+        int acc = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int m = tile / p.n_tiles;
+            const int tw = m % p.tiles_w;
+            const int th = (m / p.tiles_w) % p.tiles_h;
+            const int tn = m / m_tiles_per_img;
+            const int ow = tw * p.TW + wl;
+            const int oh = th * p.TH + hl;
+            const int n = tn * p.TN + nl;
+            const bool valid = (ow < p.OW) && (oh < p.OH) && (n < p.N);
+            const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
+
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+
+            if (p.epi == 0) {
+                const int cols_half = p.BN >> 1;
+                float ps = 1.f, pm = 1.f, om_hair = 0.f, om_back = 1.f;
+                if (valid) {
+                    if (p.pscale) ps = __ldg(p.pscale + pix);
+                    if (p.pmul) pm = __ldg(p.pmul + pix);
+                    if (p.bf) {
+                        const size_t mp = ((size_t)n * p.MH + (size_t)oh * p.mask_stride) * p.MW +
+                                          (size_t)ow * p.mask_stride;
+                        om_hair = 1.f - __ldg(p.hair + mp);
+                        om_back = 1.f - __ldg(p.back + mp);
+                    }
+                }
+                const float* resp = nullptr;
+                if (p.res && valid)
+                    resp = p.res + (((size_t)n * p.RH + (oh >> p.res_shift)) * p.RW + (ow >> p.res_shift)) * p.Cout;
+                for (int j0 = half * cols_half; j0 < (half + 1) * cols_half; j0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + j0, v);
+                    tmem_ld_wait();
+                    const int c0 = nt * p.BN + j0;
+                    if (valid && c0 < p.Cout) {
+                        float y[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]) * ps;
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                                y[i] += b.x; y[i + 1] += b.y; y[i + 2] += b.z; y[i + 3] += b.w;
+                            }
+                        }
+                        if (resp) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(resp + c0 + i));
+                                y[i] += b.x; y[i + 1] += b.y; y[i + 2] += b.z; y[i + 3] += b.w;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] = apply_act(y[i], p.act);
+                        if (p.bf) {
+                            const float* bfp = p.bf + pix * p.Cout + c0;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(bfp + i));
+                                y[i] = b.x * om_hair + y[i] * om_back;
+                                y[i + 1] = b.y * om_hair + y[i + 1] * om_back;
+                                y[i + 2] = b.z * om_hair + y[i + 2] * om_back;
+                                y[i + 3] = b.w * om_hair + y[i + 3] * om_back;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            y[i] *= pm;
+                            if (p.round_out) y[i] = round_tf32(y[i]);
+                        }
+                        float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                    }
+                }
+            } else {
+                // SPADE: columns [0,BN/2) = gamma, [BN/2,BN) = beta of channels nt*BN/2 + j
+                const int ch_tile = p.BN >> 1;
+                const int ch_half = ch_tile >> 1;
+                const float* xp = nullptr;
+                if (valid)
+                    xp = p.x + (((size_t)n * p.XH + (oh >> p.x_shift)) * p.XW + (ow >> p.x_shift)) * p.Cout;
+                for (int j0 = half * ch_half; j0 < (half + 1) * ch_half; j0 += 16) {
+                    uint32_t g[16], b[16];
+                    tmem_ld16(t_row + j0, g);
+                    tmem_ld16(t_row + ch_tile + j0, b);
+                    tmem_ld_wait();
+                    const int c0 = nt * ch_tile + j0;
+                    if (valid && c0 < p.Cout) {
+                        float y[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c0 + i));
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.nscale + c0 + i));
+                            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.nshift + c0 + i));
+                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gbias1 + c0 + i));
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bbias + c0 + i));
+                            y[i] = fmaf(fmaf(xv.x, sc.x, sh.x), g1.x + __uint_as_float(g[i]), bb.x + __uint_as_float(b[i]));
+                            y[i + 1] = fmaf(fmaf(xv.y, sc.y, sh.y), g1.y + __uint_as_float(g[i + 1]), bb.y + __uint_as_float(b[i + 1]));
+                            y[i + 2] = fmaf(fmaf(xv.z, sc.z, sh.z), g1.z + __uint_as_float(g[i + 2]), bb.z + __uint_as_float(b[i + 2]));
+                            y[i + 3] = fmaf(fmaf(xv.w, sc.w, sh.w), g1.w + __uint_as_float(g[i + 3]), bb.w + __uint_as_float(b[i + 3]));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            y[i] = apply_act(y[i], p.act);
+                            if (p.round_out) y[i] = round_tf32(y[i]);
+                        }
+                        float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int next_pow2(int v) {
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+}
+
+int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
+    if (!a || !a->in || !a->wpack || !a->out) return set_error(-1, "mg_conv_igemm: null pointer");
+    if (a->Cin % 32 != 0) return set_error(-2, "mg_conv_igemm: Cin must be a multiple of 32 (got %d)", a->Cin);
+    const int coutg = a->epi == MG_EPI_SPADE ? 2 * a->Cout : a->Cout;
+    int BN = a->BN;
+    if (BN == 0) {
+        BN = coutg >= 256 ? 256 : coutg;
+        if (a->epi == MG_EPI_SPADE && BN < 64) BN = 64;
+    }
+    if (BN % 32 != 0 || BN < 32 || BN > 256) return set_error(-3, "mg_conv_igemm: bad BN %d", BN);
+    if (coutg % BN != 0) return set_error(-4, "mg_conv_igemm: GEMM N %d not a multiple of BN %d", coutg, BN);
+    if (a->epi == MG_EPI_SPADE && (BN % 64 != 0 || !a->x || !a->nscale || !a->nshift || !a->gbias1 || !a->bbias))
+        return set_error(-5, "mg_conv_igemm: SPADE epilogue needs x/nscale/nshift/gbias1/bbias and BN%%64==0");
+    if (a->stride < 1 || a->stride > 2) return set_error(-6, "mg_conv_igemm: stride must be 1 or 2");
+    if ((a->bf != nullptr) && (!a->hair || !a->back)) return set_error(-7, "mg_conv_igemm: blend needs hair/back");
+
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = a->N; p.OH = a->OH; p.OW = a->OW; p.Cout = a->Cout;
+    p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.stride = a->stride; p.pad = a->pad;
+    p.TW = next_pow2(a->OW) < 16 ? next_pow2(a->OW) : 16;
+    int th = 128 / p.TW;
+    p.TH = next_pow2(a->OH) < th ? next_pow2(a->OH) : th;
+    p.TN = 128 / (p.TW * p.TH);
+    p.tiles_w = (a->OW + p.TW - 1) / p.TW;
+    p.tiles_h = (a->OH + p.TH - 1) / p.TH;
+    p.tiles_n = (a->N + p.TN - 1) / p.TN;
+    p.BN = BN;
+    p.n_tiles = coutg / BN;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+    p.kchunks = a->Cin / 32;
+    const int stage_bytes = kABytes + BN * 128;
+    int stages = (220 * 1024) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+    p.idesc = umma_idesc_tf32(128, BN);
+    int tc = next_pow2(2 * BN);
+    p.tmem_cols = tc < 32 ? 32 : tc;
+    p.epi = a->epi; p.act = a->act; p.round_out = a->round_out;
+    p.out = a->out; p.bias = a->bias;
+    p.res = a->res; p.res_shift = a->res_shift;
+    p.RH = a->OH >> a->res_shift; p.RW = a->OW >> a->res_shift;
+    p.pscale = a->pscale; p.pmul = a->pmul;
+    p.bf = a->bf; p.hair = a->hair; p.back = a->back;
+    p.mask_stride = a->mask_stride; p.MH = a->MH; p.MW = a->MW;
+    p.x = a->x; p.x_shift = a->x_shift; p.XH = a->OH >> a->x_shift; p.XW = a->OW >> a->x_shift;
+    p.nscale = a->nscale; p.nshift = a->nshift; p.gbias1 = a->gbias1; p.bbias = a->bbias;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+        cuuint64_t strides[3] = {(cuuint64_t)a->Cin * 4, (cuuint64_t)a->W * a->Cin * 4,
+                                 (cuuint64_t)a->H * a->W * a->Cin * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * a->stride), (cuuint32_t)(p.TH * a->stride), (cuuint32_t)p.TN};
+        cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
+        int rc = encode_tensor_map(&tmA, (void*)a->in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)a->KH * a->KW * a->Cin;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)coutg};
+        cuuint64_t strides[1] = {ktot * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        int rc = encode_tensor_map(&tmB, (void*)a->wpack, 2, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static thread_local int attr_set_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_set_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set_dev = dev;
+    }
+    int grid = num_sms();
+    if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    igemm_tf32_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error((int)e, "igemm launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace mg
+
+extern "C" int mg_conv_igemm(const mg_igemm_args* a, void* stream) {
+    return mg::igemm_launch(a, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,275 @@
+"""Functional wrappers: torch CUDA tensors in, C-ABI calls on the current stream, torch tensors out.
+
+PyTorch is plumbing here (device memory, streams); every arithmetic op below runs in
+libmichigan_sm100.so.  Activations are NHWC fp32 ([N,H,W,C] contiguous).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import IgemmArgs, ThinArgs, check
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+EPI_BIAS, EPI_SPADE = 0, 1
+
+
+def _p(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.MichiganNativeError("%s must be a CUDA tensor (no CPU path exists)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+
+
+def spade_bn(c):
+    """GEMM N tile used for a gamma|beta operand of `c` channels (must match the weight packing)."""
+    return 256 if 2 * c >= 256 else max(64, 2 * c)
+
+
+# ------------------------------------------------------------------------------------------ weights
+def pack_weight(w_oihw, inv_sigma=None, round_tf32=True):
+    _chk(w_oihw, "w"); _chk(inv_sigma, "inv_sigma")
+    O, I, KH, KW = w_oihw.shape
+    out = torch.empty((O, KH * KW * I), device=w_oihw.device, dtype=torch.float32)
+    check(_lib.load().mg_pack_weight(_p(w_oihw), _p(out), O, I, KH, KW, _p(inv_sigma), int(round_tf32), _stream()),
+          "mg_pack_weight")
+    return out
+
+
+def pack_weight_gb(wg, wb):
+    _chk(wg, "wg"); _chk(wb, "wb")
+    Cc, I, KH, KW = wg.shape
+    bn = spade_bn(Cc)
+    out = torch.empty((2 * Cc, KH * KW * I), device=wg.device, dtype=torch.float32)
+    check(_lib.load().mg_pack_weight_gb(_p(wg), _p(wb), _p(out), Cc, I, KH, KW, bn, _stream()), "mg_pack_weight_gb")
+    return out
+
+
+def pack_weight_thin(w_oihw, cin_pad):
+    _chk(w_oihw, "w")
+    O, I, KH, KW = w_oihw.shape
+    out = torch.empty((KH * KW, cin_pad, O), device=w_oihw.device, dtype=torch.float32)
+    check(_lib.load().mg_pack_weight_thin(_p(w_oihw), _p(out), O, I, cin_pad, KH, KW, _stream()), "mg_pack_weight_thin")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ convs
+def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_out=False, bias=None, res=None,
+               res_shift=0, pscale=None, pmul=None, blend=None, spade=None, bn=0, max_ctas=0):
+    """Implicit-GEMM conv on tcgen05.  x: [N,H,W,Cin]; returns [N,OH,OW,cout].
+
+    blend = (bf[N,OH,OW,cout], hair[N,MH,MW], back[N,MH,MW], mask_stride)
+    spade = (xsrc[N,OH>>s,OW>>s,cout], x_shift, nscale[c], nshift[c], gbias1[c], bbias[c])
+    """
+    _chk(x, "x"); _chk(wpack, "wpack"); _chk(bias, "bias"); _chk(res, "res"); _chk(pscale, "pscale"); _chk(pmul, "pmul")
+    N, H, W, Cin = x.shape
+    OH = (H + 2 * pad - kh) // stride + 1
+    OW = (W + 2 * pad - kw) // stride + 1
+    out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32)
+    a = IgemmArgs()
+    a.inp, a.wpack, a.out = _p(x), _p(wpack), _p(out)
+    a.N, a.H, a.W, a.Cin = N, H, W, Cin
+    a.OH, a.OW, a.Cout = OH, OW, cout
+    a.KH, a.KW, a.stride, a.pad = kh, kw, stride, pad
+    a.BN = bn
+    a.epi = EPI_SPADE if spade is not None else EPI_BIAS
+    a.act, a.round_out = act, int(round_out)
+    a.bias, a.res, a.res_shift = _p(bias), _p(res), res_shift
+    a.pscale, a.pmul = _p(pscale), _p(pmul)
+    if res is not None:
+        assert tuple(res.shape) == (N, OH >> res_shift, OW >> res_shift, cout), (res.shape, out.shape, res_shift)
+    if blend is not None:
+        bf, hair, back, ms = blend
+        _chk(bf, "bf"); _chk(hair, "hair"); _chk(back, "back")
+        assert tuple(bf.shape) == (N, OH, OW, cout), (bf.shape, out.shape)
+        a.bf, a.hair, a.back = _p(bf), _p(hair), _p(back)
+        a.mask_stride, a.MH, a.MW = ms, hair.shape[-2], hair.shape[-1]
+    if spade is not None:
+        xs, x_shift, nscale, nshift, gbias1, bbias = spade
+        for t, nm in ((xs, "spade.x"), (nscale, "nscale"), (nshift, "nshift"), (gbias1, "gbias1"), (bbias, "bbias")):
+            _chk(t, nm)
+        assert tuple(xs.shape) == (N, OH >> x_shift, OW >> x_shift, cout), (xs.shape, out.shape, x_shift)
+        assert wpack.shape[0] == 2 * cout
+        a.x, a.x_shift = _p(xs), x_shift
+        a.nscale, a.nshift, a.gbias1, a.bbias = _p(nscale), _p(nshift), _p(gbias1), _p(bbias)
+        if bn == 0:
+            a.BN = spade_bn(cout)
+    else:
+        assert wpack.shape[0] == cout, (wpack.shape, cout)
+    assert wpack.shape[1] == kh * kw * Cin, (wpack.shape, kh, kw, Cin)
+    a.max_ctas = max_ctas
+    check(_lib.load().mg_conv_igemm(C.byref(a), _stream()), "mg_conv_igemm")
+    return out
+
+
+def conv_thin(x, wt, bias, cout, kh, kw, stride=1, pad=0, *, pad_mode=0, seg_resize=0, act=ACT_NONE, round_out=False,
+              pscale=None, pmul=None, out_hw=None):
+    """Direct conv for 3/4/7-channel inputs (channels padded to 4 or 8).  x: [N,H,W,CinP]."""
+    _chk(x, "x"); _chk(wt, "wt"); _chk(bias, "bias"); _chk(pscale, "pscale"); _chk(pmul, "pmul")
+    N, Hp, Wp, CinP = x.shape
+    if seg_resize:
+        H, W = out_hw  # virtual (resized) input == output size for the 3x3/pad1 SPADE conv
+    else:
+        H, W = Hp, Wp
+    OH = (H + 2 * pad - kh) // stride + 1
+    OW = (W + 2 * pad - kw) // stride + 1
+    out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32)
+    a = ThinArgs()
+    a.inp, a.w, a.bias, a.out = _p(x), _p(wt), _p(bias), _p(out)
+    a.N, a.H, a.W, a.CinP = N, H, W, CinP
+    a.OH, a.OW, a.Cout = OH, OW, cout
+    a.KH, a.KW, a.stride, a.pad = kh, kw, stride, pad
+    a.pad_mode, a.seg_resize = pad_mode, seg_resize
+    a.act, a.round_out = act, int(round_out)
+    a.pscale, a.pmul = _p(pscale), _p(pmul)
+    check(_lib.load().mg_conv_thin(C.byref(a), _stream()), "mg_conv_thin")
+    return out
+
+
+def conv_img(x, w_oihw, bias, act_in=ACT_LRELU, act_out=ACT_TANH):
+    _chk(x, "x"); _chk(w_oihw, "w"); _chk(bias, "bias")
+    N, H, W, Cin = x.shape
+    cout = w_oihw.shape[0]
+    out = torch.empty((N, cout, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_conv_img(_p(x), _p(w_oihw), _p(bias), _p(out), N, H, W, Cin, cout, act_in, act_out, _stream()),
+          "mg_conv_img")
+    return out
+
+
+def conv_to1(x, w_oihw, bias, pad):
+    _chk(x, "x"); _chk(w_oihw, "w"); _chk(bias, "bias")
+    N, H, W, Cin = x.shape
+    _, _, KH, KW = w_oihw.shape
+    OH, OW = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
+    out = torch.empty((N, OH, OW, 1), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_conv_to1(_p(x), _p(w_oihw), _p(bias), _p(out), N, H, W, Cin, KH, KW, pad, _stream()), "mg_conv_to1")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ norms
+def bn_sums(x):
+    """Per-channel (sum, sum of squares) of an NHWC tensor as a [2*C] float64 tensor."""
+    _chk(x, "x")
+    Cc = x.shape[-1]
+    sums = torch.zeros(2 * Cc, device=x.device, dtype=torch.float64)
+    check(_lib.load().mg_bn_stats(_p(x), x.numel() // Cc, Cc, _p(sums), _stream()), "mg_bn_stats")
+    return sums
+
+
+def bn_finalize(sums, count, count_unbiased, eps=1e-5, momentum=0.1, clamp_mode=0, running_mean=None, running_var=None,
+                want_stats=False):
+    Cc = sums.numel() // 2
+    nscale = torch.empty(Cc, device=sums.device, dtype=torch.float32)
+    nshift = torch.empty(Cc, device=sums.device, dtype=torch.float32)
+    mean = torch.empty(Cc, device=sums.device, dtype=torch.float32) if want_stats else None
+    var = torch.empty(Cc, device=sums.device, dtype=torch.float32) if want_stats else None
+    _chk(running_mean, "running_mean"); _chk(running_var, "running_var")
+    check(_lib.load().mg_bn_finalize(_p(sums), Cc, float(count), float(count_unbiased), eps, momentum, clamp_mode,
+                                     _p(nscale), _p(nshift), _p(running_mean), _p(running_var), _p(mean), _p(var),
+                                     _stream()), "mg_bn_finalize")
+    if want_stats:
+        return nscale, nshift, mean, var
+    return nscale, nshift
+
+
+def bn_from_running(running_mean, running_var, eps=1e-5):
+    _chk(running_mean, "running_mean"); _chk(running_var, "running_var")
+    Cc = running_mean.numel()
+    nscale = torch.empty(Cc, device=running_mean.device, dtype=torch.float32)
+    nshift = torch.empty(Cc, device=running_mean.device, dtype=torch.float32)
+    check(_lib.load().mg_bn_from_running(_p(running_mean), _p(running_var), Cc, eps, _p(nscale), _p(nshift), _stream()),
+          "mg_bn_from_running")
+    return nscale, nshift
+
+
+def instance_norm_act(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None):
+    """InstanceNorm2d(affine=False) followed by an activation, NHWC."""
+    _chk(x, "x"); _chk(pmul, "pmul")
+    N, H, W, Cc = x.shape
+    sums = torch.zeros((N, 2, Cc), device=x.device, dtype=torch.float64)
+    lib = _lib.load()
+    check(lib.mg_in_stats(_p(x), N, H * W, Cc, _p(sums), _stream()), "mg_in_stats")
+    ss = torch.empty((N, 2, Cc), device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    check(lib.mg_in_apply(_p(x), _p(sums), _p(ss), _p(y), N, H * W, Cc, eps, act, int(round_out), _p(pmul), _stream()),
+          "mg_in_apply")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ prep / pooling
+def prep_seg(tag_nchw, orient_nchw):
+    _chk(tag_nchw, "input_tag"); _chk(orient_nchw, "orient")
+    N, _, H, W = tag_nchw.shape
+    oc = orient_nchw.shape[1]
+    seg4 = torch.empty((N, H, W, 4), device=tag_nchw.device, dtype=torch.float32)
+    check(_lib.load().mg_prep_seg(_p(tag_nchw), _p(orient_nchw), oc, _p(seg4), N, H, W, _stream()), "mg_prep_seg")
+    return seg4
+
+
+def prep_dinput(seg4, img_nchw):
+    _chk(seg4, "seg4"); _chk(img_nchw, "image")
+    N, H, W, _ = seg4.shape
+    out = torch.empty((N, H, W, 8), device=seg4.device, dtype=torch.float32)
+    check(_lib.load().mg_prep_dinput(_p(seg4), _p(img_nchw), _p(out), N, H, W, _stream()), "mg_prep_dinput")
+    return out
+
+
+def prep_bginput(img_nchw, noise_nchw, back):
+    _chk(img_nchw, "image"); _chk(noise_nchw, "noise"); _chk(back, "back_mask")
+    N, _, H, W = img_nchw.shape
+    out = torch.empty((N, H, W, 4), device=img_nchw.device, dtype=torch.float32)
+    check(_lib.load().mg_prep_bginput(_p(img_nchw), _p(noise_nchw), _p(back), _p(out), N, H, W, _stream()),
+          "mg_prep_bginput")
+    return out
+
+
+def nchw_to_nhwc(x, cpad=None):
+    _chk(x, "x")
+    N, Cc, H, W = x.shape
+    cp = cpad or Cc
+    out = torch.empty((N, H, W, cp), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_nchw_to_nhwc(_p(x), _p(out), N, Cc, H, W, cp, _stream()), "mg_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, c=None):
+    _chk(x, "x")
+    N, H, W, cp = x.shape
+    Cc = c or cp
+    out = torch.empty((N, Cc, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_nhwc_to_nchw(_p(x), _p(out), N, Cc, H, W, cp, _stream()), "mg_nhwc_to_nchw")
+    return out
+
+
+def maxpool_mask(m, k, invert=False):
+    """max_pool2d(k, stride 1, pad k//2) of a [N,H,W] map; invert -> 1 - pooled."""
+    _chk(m, "mask")
+    N, H, W = m.shape
+    out = torch.empty_like(m)
+    tmp = torch.empty_like(m)
+    check(_lib.load().mg_maxpool_mask(_p(m), _p(out), _p(tmp), N, H, W, k, int(invert), _stream()), "mg_maxpool_mask")
+    return out
+
+
+def avgpool3s2(x):
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = torch.empty((N, OH, OW, Cc), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_avgpool3s2(_p(x), _p(out), N, H, W, Cc, OH, OW, _stream()), "mg_avgpool3s2")
+    return out

@@ -1,0 +1,273 @@
+"""Development probe (GPU box): every C-ABI kernel against torch-on-GPU fp32 with TF32 disabled.
+
+    python tools/probe_kernels.py <group>      groups: igemm igemm2 spade thin misc perf
+
+Each group runs in its own process (a faulting kernel poisons the CUDA context).  Not a parity test:
+tests/ compare against the CPU oracle; this is a fast bring-up/diagnostic tool.
+"""
+import sys
+import os
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+from michigan_b200 import ops  # noqa: E402
+
+dev = "cuda"
+FAILS = []
+
+
+def tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def report(name, got, ref, tol):
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    ok = err <= tol * max(scale, 1e-6)
+    print("%-58s max|err| %.3e  ref max %.3e  %s" % (name, err, scale, "OK" if ok else "FAIL"), flush=True)
+    if not ok:
+        FAILS.append(name)
+        d = (got - ref).abs()
+        idx = torch.nonzero(d > tol * max(scale, 1e-6))
+        print("   bad elements: %d / %d ; first: %s" % (idx.shape[0], d.numel(), idx[:5].tolist()))
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def igemm_case(N, H, W, Cin, Cout, k, s, p, bias=True, act=0, exact=True, tol=2e-5, bn=0, name=None):
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + H * 10 + Cin + Cout + k)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev) if bias else None
+    if exact:
+        x = tf32_trunc(x)
+        w = tf32_trunc(w)
+    ref = F.conv2d(x, w, b, stride=s, padding=p)
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    wp = ops.pack_weight(w, None, round_tf32=True)
+    got = ops.conv_igemm(nhwc(x), wp, Cout, k, k, s, p, bias=b, act=act, bn=bn)
+    torch.cuda.synchronize()
+    report(name or "igemm N%d %dx%d %d->%d k%d s%d p%d bn%d" % (N, H, W, Cin, Cout, k, s, p, bn), nchw(got), ref, tol)
+
+
+def group_igemm():
+    igemm_case(2, 32, 32, 64, 64, 3, 1, 1)
+    igemm_case(1, 16, 16, 32, 32, 1, 1, 0)
+    igemm_case(2, 32, 32, 128, 256, 3, 1, 1)
+    igemm_case(1, 64, 64, 64, 128, 3, 1, 1, bn=64)
+    igemm_case(2, 16, 16, 256, 512, 3, 1, 1)
+
+
+def group_igemm2():
+    igemm_case(3, 8, 8, 64, 64, 3, 1, 1)          # two images per tile, ragged batch
+    igemm_case(5, 4, 4, 64, 32, 3, 1, 1)          # eight images per tile
+    igemm_case(2, 33, 33, 64, 128, 4, 2, 2, bias=False)   # PatchGAN geometry, stride 2 via elementStrides
+    igemm_case(2, 65, 65, 64, 128, 4, 1, 2, bias=False)   # stride 1 pad 2 (model3)
+    igemm_case(2, 66, 66, 64, 64, 4, 2, 1, bias=True, act=1 if False else 0)  # k4 s2 p1 (bg encoder after pad)
+    igemm_case(2, 64, 64, 64, 128, 3, 2, 1)       # partial-conv geometry
+    igemm_case(2, 32, 32, 64, 64, 3, 1, 1, exact=False, tol=3e-3, name="igemm unrounded inputs (tf32 hw rounding)")
+    # larger: multiple tiles per CTA (persistence + both TMEM buffers + ring wrap)
+    igemm_case(4, 128, 128, 128, 256, 3, 1, 1)
+
+
+def group_spade():
+    g = torch.Generator(device="cpu").manual_seed(7)
+    for (N, h, C, xs) in ((2, 32, 64, 0), (2, 32, 128, 1), (1, 64, 32, 0), (3, 8, 256, 1)):
+        actv = tf32_trunc(torch.randn(N, 128, h, h, generator=g).to(dev))
+        wg = tf32_trunc((torch.randn(C, 128, 3, 3, generator=g) / 34.0).to(dev))
+        wb = tf32_trunc((torch.randn(C, 128, 3, 3, generator=g) / 34.0).to(dev))
+        bg = torch.randn(C, generator=g).to(dev) * 0.1
+        bb = torch.randn(C, generator=g).to(dev) * 0.1
+        xh = h >> xs
+        x = torch.randn(N, C, xh, xh, generator=g).to(dev)
+        mean = torch.randn(C, generator=g).to(dev) * 0.1
+        rstd = (torch.rand(C, generator=g).to(dev) + 0.5)
+        gamma = F.conv2d(actv, wg, bg, padding=1)
+        beta = F.conv2d(actv, wb, bb, padding=1)
+        xu = F.interpolate(x, scale_factor=2 ** xs, mode="nearest") if xs else x
+        ref = F.leaky_relu((xu - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1) * (1 + gamma) + beta, 0.2)
+        wp = ops.pack_weight_gb(wg, wb)
+        got = ops.conv_igemm(nhwc(actv), wp, C, 3, 3, 1, 1, act=2,
+                             spade=(nhwc(x), xs, rstd.contiguous(), (-mean * rstd).contiguous(), (1 + bg).contiguous(), bb))
+        torch.cuda.synchronize()
+        report("spade N%d %dx%d C%d xshift%d" % (N, h, h, C, xs), nchw(got), ref, 3e-5)
+    # residual (upsampled source) + blend epilogue
+    N, h, Cin, Cout = 2, 32, 64, 64
+    x = tf32_trunc(torch.randn(N, Cin, h, h, generator=g).to(dev))
+    w = tf32_trunc((torch.randn(Cout, Cin, 3, 3, generator=g) / 24.0).to(dev))
+    b = torch.randn(Cout, generator=g).to(dev)
+    res = torch.randn(N, Cout, h // 2, h // 2, generator=g).to(dev)
+    bf = torch.randn(N, Cout, h, h, generator=g).to(dev)
+    hair = (torch.rand(N, 4 * h, 4 * h, generator=g) > 0.5).float().to(dev)
+    back = (torch.rand(N, 4 * h, 4 * h, generator=g) > 0.5).float().to(dev)
+    y = F.conv2d(x, w, b, padding=1) + F.interpolate(res, scale_factor=2, mode="nearest")
+    hs = hair[:, ::4, ::4].unsqueeze(1)
+    bs = back[:, ::4, ::4].unsqueeze(1)
+    ref = bf * (1 - hs) + y * (1 - bs)
+    got = ops.conv_igemm(nhwc(x), ops.pack_weight(w), Cout, 3, 3, 1, 1, bias=b, res=nhwc(res), res_shift=1,
+                         blend=(nhwc(bf), hair, back, 4))
+    torch.cuda.synchronize()
+    report("igemm residual(up2)+blend", nchw(got), ref, 3e-5)
+    # per-pixel scales (partial conv)
+    ps = torch.rand(N, h, h, generator=g).to(dev) + 0.5
+    pm = (torch.rand(N, h, h, generator=g) > 0.3).float().to(dev)
+    ref = (F.conv2d(x, w, None, padding=1) * ps.unsqueeze(1) + b.view(1, -1, 1, 1)) * pm.unsqueeze(1)
+    got = ops.conv_igemm(nhwc(x), ops.pack_weight(w), Cout, 3, 3, 1, 1, bias=b, pscale=ps, pmul=pm)
+    torch.cuda.synchronize()
+    report("igemm pscale/pmul (partial conv)", nchw(got), ref, 3e-5)
+
+
+def group_thin():
+    g = torch.Generator(device="cpu").manual_seed(11)
+    # SPADE mlp_shared with nearest-resized seg
+    N, Hf = 2, 64
+    seg = torch.randn(N, 4, Hf, Hf, generator=g).to(dev)
+    w = (torch.randn(128, 4, 3, 3, generator=g) / 6).to(dev)
+    b = torch.randn(128, generator=g).to(dev)
+    for h in (64, 32, 8):
+        s_r = F.interpolate(seg, size=(h, h), mode="nearest")
+        ref = F.relu(F.conv2d(s_r, w, b, padding=1))
+        got = ops.conv_thin(nhwc(seg), ops.pack_weight_thin(w, 4), b, 128, 3, 3, 1, 1, seg_resize=Hf // h, act=1,
+                            out_hw=(h, h))
+        torch.cuda.synchronize()
+        report("thin mlp_shared seg %d->%d" % (Hf, h), nchw(got), ref, 1e-5)
+    # k7 reflect 3->64
+    x = torch.randn(N, 3, 40, 40, generator=g).to(dev)
+    w = (torch.randn(64, 3, 7, 7, generator=g) / 12).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    ref = F.relu(F.conv2d(F.pad(x, (3, 3, 3, 3), mode="reflect"), w, b))
+    got = ops.conv_thin(ops.nchw_to_nhwc(x, 4), ops.pack_weight_thin(w, 4), b, 64, 7, 7, 1, 3, pad_mode=1, act=1)
+    torch.cuda.synchronize()
+    report("thin k7 reflect 3->64", nchw(got), ref, 1e-5)
+    # D layer 0: 7->64 k4 s2 p2 lrelu
+    x = torch.randn(N, 7, 64, 64, generator=g).to(dev)
+    w = (torch.randn(64, 7, 4, 4, generator=g) / 10).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    ref = F.leaky_relu(F.conv2d(x, w, b, stride=2, padding=2), 0.2)
+    got = ops.conv_thin(ops.nchw_to_nhwc(x, 8), ops.pack_weight_thin(w, 8), b, 64, 4, 4, 2, 2, act=2)
+    torch.cuda.synchronize()
+    report("thin D0 7->64 k4 s2 p2", nchw(got), ref, 1e-5)
+    # partial conv layer 1: 3->64 k3 s2 p1
+    x = torch.randn(N, 3, 64, 64, generator=g).to(dev)
+    w = (torch.randn(64, 3, 3, 3, generator=g) / 5).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    ref = F.conv2d(x, w, b, stride=2, padding=1)
+    got = ops.conv_thin(ops.nchw_to_nhwc(x, 4), ops.pack_weight_thin(w, 4), b, 64, 3, 3, 2, 1)
+    torch.cuda.synchronize()
+    report("thin 3->64 k3 s2 p1", nchw(got), ref, 1e-5)
+
+
+def group_misc():
+    g = torch.Generator(device="cpu").manual_seed(13)
+    N = 2
+    x = torch.randn(N, 64, 48, 40, generator=g).to(dev)
+    w = (torch.randn(3, 64, 3, 3, generator=g) / 24).to(dev)
+    b = torch.randn(3, generator=g).to(dev)
+    ref = torch.tanh(F.conv2d(F.leaky_relu(x, 0.2), w, b, padding=1))
+    got = ops.conv_img(nhwc(x), w, b)
+    torch.cuda.synchronize()
+    report("conv_img", got, ref, 1e-5)
+    x = torch.randn(N, 128, 18, 18, generator=g).to(dev)
+    w = (torch.randn(1, 128, 4, 4, generator=g) / 45).to(dev)
+    b = torch.randn(1, generator=g).to(dev)
+    ref = F.conv2d(x, w, b, padding=2)
+    got = ops.conv_to1(nhwc(x), w, b, 2)
+    torch.cuda.synchronize()
+    report("conv_to1", nchw(got), ref, 1e-5)
+    # BN stats
+    for C_, hw in ((64, 64), (1024, 8), (96, 20)):
+        x = torch.randn(3, C_, hw, hw, generator=g).to(dev) * 2 + 0.7
+        sums = ops.bn_sums(nhwc(x))
+        cnt = 3 * hw * hw
+        rm = torch.zeros(C_, device=dev); rv = torch.ones(C_, device=dev)
+        nscale, nshift, mean, var = ops.bn_finalize(sums, cnt, cnt * 4, running_mean=rm, running_var=rv, want_stats=True)
+        torch.cuda.synchronize()
+        xd = x.double()
+        m_ref = xd.mean(dim=(0, 2, 3)); v_ref = xd.var(dim=(0, 2, 3), unbiased=False)
+        report("bn mean C%d" % C_, mean.double(), m_ref, 1e-6)
+        report("bn var C%d" % C_, var.double(), v_ref, 1e-6)
+        report("bn nscale C%d" % C_, nscale.double(), 1 / torch.sqrt(v_ref + 1e-5), 1e-6)
+        report("bn running_var C%d" % C_, rv.double(), 0.9 + 0.1 * v_ref * (4 * cnt) / (4 * cnt - 1), 1e-6)
+    # instance norm + lrelu
+    x = torch.randn(3, 128, 33, 33, generator=g).to(dev) * 3 + 1
+    ref = F.leaky_relu(F.instance_norm(x), 0.2)
+    got = ops.instance_norm_act(nhwc(x))
+    torch.cuda.synchronize()
+    report("instance_norm+lrelu", nchw(got), ref, 1e-5)
+    # prep
+    tag = (torch.rand(N, 2, 32, 32, generator=g) > 0.5).float().to(dev)
+    ori = torch.floor(torch.rand(N, 1, 32, 32, generator=g) * 255).to(dev)
+    th = ori / 255.0 * 3.141592653589793
+    ref = torch.cat([tag, torch.sin(2 * th) * tag[:, 1:2], torch.cos(2 * th) * tag[:, 1:2]], 1)
+    seg4 = ops.prep_seg(tag, ori)
+    torch.cuda.synchronize()
+    report("prep_seg", nchw(seg4), ref, 2e-6)
+    img = torch.randn(N, 3, 32, 32, generator=g).to(dev)
+    d8 = ops.prep_dinput(seg4, img)
+    report("prep_dinput", nchw(d8)[:, :7], torch.cat([ref, img], 1), 2e-6)
+    noise = torch.rand(N, 3, 32, 32, generator=g).to(dev)
+    hair = tag[:, 1].contiguous()
+    back = ops.maxpool_mask(hair, 5, invert=True)
+    ref_back = 1 - F.max_pool2d(hair.unsqueeze(1), 5, 1, 2)
+    report("maxpool_mask", back.unsqueeze(1), ref_back, 0)
+    bgin = ops.prep_bginput(img, noise, back)
+    report("prep_bginput", nchw(bgin)[:, :3], img * ref_back + noise * (1 - ref_back), 1e-6)
+    x8 = torch.randn(N, 8, 33, 31, generator=g).to(dev)
+    ref = F.avg_pool2d(x8, 3, 2, [1, 1], count_include_pad=False)
+    report("avgpool3s2", nchw(ops.avgpool3s2(nhwc(x8))), ref, 1e-6)
+    report("nhwc_to_nchw", ops.nhwc_to_nchw(nhwc(x8)), x8, 0)
+
+
+def group_perf():
+    # first timing of the headline GEMM shapes (up_3 gamma/beta and conv_0 at 512x512, N=8)
+    from michigan_b200 import _lib
+    for (N, h, Cin, C, spade) in ((8, 512, 128, 128, True), (8, 512, 128, 64, False), (8, 256, 128, 256, True),
+                                  (8, 128, 128, 512, True), (8, 64, 1024, 512, False)):
+        x = torch.randn(N, h, h, Cin, device=dev)
+        if spade:
+            wg = torch.randn(C, Cin, 3, 3, device=dev) / 34
+            wp = ops.pack_weight_gb(wg, wg)
+            xs = torch.randn(N, h, h, C, device=dev)
+            v = torch.ones(C, device=dev)
+            args = dict(act=2, spade=(xs, 0, v, v, v, v), round_out=True)
+            flops = 2.0 * N * h * h * 9 * Cin * 2 * C
+        else:
+            w = torch.randn(C, Cin, 3, 3, device=dev) / 34
+            wp = ops.pack_weight(w)
+            args = dict(bias=torch.zeros(C, device=dev))
+            flops = 2.0 * N * h * h * 9 * Cin * C
+        for _ in range(2):
+            ops.conv_igemm(x, wp, C, 3, 3, 1, 1, **args)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.conv_igemm(x, wp, C, 3, 3, 1, 1, **args)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("perf N%d %dx%d Cin%d C%d spade=%d: %.3f ms  %.1f TFLOP/s" % (N, h, h, Cin, C, spade, ms, flops / ms / 1e9),
+              flush=True)
+
+
+if __name__ == "__main__":
+    grp = sys.argv[1]
+    t0 = time.time()
+    print("== group %s on %s" % (grp, torch.cuda.get_device_name(0)), flush=True)
+    globals()["group_" + grp]()
+    torch.cuda.synchronize()
+    print("== group %s done in %.1fs, failures: %s" % (grp, time.time() - t0, FAILS), flush=True)
+    sys.exit(1 if FAILS else 0)
