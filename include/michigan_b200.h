@@ -148,13 +148,42 @@ int mg_prep_dinput(const float* seg4, const float* img_nchw, float* out8, int N,
 /* background-encoder input (encoder.py:321): img*back + noise*(1-back) -> [N,H,W,4]. */
 int mg_prep_bginput(const float* img_nchw, const float* noise_nchw, const float* back, float* out4, int N, int H,
                     int W, void* stream);
-/* NCHW [N,C,H,W] -> NHWC with channel padding to CP. */
-int mg_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, int CP, void* stream);
+/* NCHW [N,C,H,W] -> NHWC with channel padding to CP; optional per-pixel multiplier pmul [N,H,W]
+ * (the `input * mask` of partialconv2d.py:69). */
+int mg_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, int CP, const float* pmul, void* stream);
 int mg_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, int CP, void* stream);
 /* max_pool2d(k, stride 1, pad k/2) on a 1-channel map (encoder.py:296,310-313); out = 1 - pool if invert. */
 int mg_maxpool_mask(const float* in, float* out, float* tmp, int N, int H, int W, int k, int invert, void* stream);
 /* avg_pool2d(k3,s2,p1,count_include_pad=False) on NHWC (discriminator.py:46-49). */
 int mg_avgpool3s2(const float* in, float* out, int N, int H, int W, int C, int OH, int OW, void* stream);
+
+/* PartialConv2d mask update (partialconv2d.py:57-66): mask [N,H,W] -> ratio, update [N,OH,OW]. */
+int mg_partial_mask(const float* mask, float* ratio, float* update, int N, int H, int W, int k, int stride, int pad,
+                    void* stream);
+/* ImageEncoder3 instance-wise average pooling (encoder.py:207-220); masks are [N,MH,MW] full-res. */
+int mg_masked_mean_bcast(const float* x, const float* mref, const float* mtag, float* out, int N, int h, int w, int C,
+                         int MH, int MW, void* stream);
+/* F.interpolate(bilinear, align_corners=False) on NHWC (encoder.py:222-223). */
+int mg_resize_bilinear(const float* in, float* out, int N, int H, int W, int C, int OH, int OW, void* stream);
+/* nn.ReflectionPad2d(pad) on NHWC (MaskGAN_networks.py:120-121), optional TF32 (RNA) rounding. */
+int mg_reflect_pad(const float* in, float* out, int N, int H, int W, int C, int pad, int round_tf32, void* stream);
+
+/* Spectral norm for all SN convs of a network in three launches (torch SpectralNorm.compute_weight
+ * as applied at architecture.py:38-42, normalization.py:28-29).  `descs` is a DEVICE array of
+ * mg_sn_desc.  training != 0: one in-place power iteration (v = normalize(W^T u), u = normalize(W v),
+ * eps 1e-12) then inv_sigma = 1/(u^T W v); training == 0: inv_sigma from the stored u, v.
+ * The `t` workspace must be zero on entry and is left zeroed. */
+typedef struct mg_sn_desc {
+    const float* w;   /* [O][K] weight_orig viewed as a matrix */
+    float* u;         /* [O] weight_u */
+    float* v;         /* [K] weight_v */
+    float* t;         /* [K] workspace */
+    float* s;         /* [O] workspace */
+    float* inv_sigma; /* [1] */
+    int32_t O, K;
+} mg_sn_desc;
+int mg_spectral_norm_batched(const void* descs, int n_layers, int max_O, int max_K, int training, float eps,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,12 @@ SIGNATURES = {
     "mg_prep_seg": [_p, _p, _i, _p, _i, _i, _i, _p],
     "mg_prep_dinput": [_p, _p, _p, _i, _i, _i, _p],
     "mg_prep_bginput": [_p, _p, _p, _p, _i, _i, _i, _p],
-    "mg_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "mg_partial_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_masked_mean_bcast": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_resize_bilinear": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_reflect_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_spectral_norm_batched": [_p, _i, _i, _i, _i, _f, _p],
     "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -475,7 +475,7 @@ __global__ void prep_bginput_kernel(const float* __restrict__ img, const float* 
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, long long HW,
-                                    int CP) {
+                                    int CP, const float* __restrict__ pmul) {
     const long long total = (long long)N * HW * CP;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -483,7 +483,114 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
         const long long pix = idx / CP;
         const int n = pix / HW;
         const long long p = pix - (long long)n * HW;
-        out[idx] = c < C ? in[((size_t)n * C + c) * HW + p] : 0.f;
+        out[idx] = c < C ? in[((size_t)n * C + c) * HW + p] * (pmul ? pmul[pix] : 1.f) : 0.f;
+    }
+}
+
+// PartialConv2d mask bookkeeping (partialconv2d.py:57-66), single-channel mask [N,H,W]:
+// um = sum of mask over the k x k window (zero padded); ratio = k*k/(um+1e-8)*clamp(um,0,1); update = clamp(um,0,1)
+__global__ void partial_mask_kernel(const float* __restrict__ mask, float* __restrict__ ratio, float* __restrict__ update,
+                                    int N, int H, int W, int OH, int OW, int k, int s, int p) {
+    const long long total = (long long)N * OH * OW;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ow = idx % OW;
+        const int oh = (idx / OW) % OH;
+        const int n = idx / ((long long)OW * OH);
+        float um = 0.f;
+        for (int kh = 0; kh < k; ++kh) {
+            const int ih = oh * s + kh - p;
+            if (ih < 0 || ih >= H) continue;
+            for (int kw = 0; kw < k; ++kw) {
+                const int iw = ow * s + kw - p;
+                if (iw < 0 || iw >= W) continue;
+                um += mask[((size_t)n * H + ih) * W + iw];
+            }
+        }
+        const float r = (float)(k * k) / (um + 1e-8f);
+        const float u = fminf(fmaxf(um, 0.f), 1.f);
+        ratio[idx] = r * u;
+        update[idx] = u;
+    }
+}
+
+// ImageEncoder3 tail (encoder.py:207-220): per sample, mean of x over the reference-hair pixels
+// (sum / max(count,1)), broadcast onto the target-hair pixels.  Masks are full-resolution [N,MH,MW]
+// read through the legacy nearest resize (index * MH/h).  One block per (n, 32-channel group).
+__global__ void masked_mean_bcast_kernel(const float* __restrict__ x, const float* __restrict__ mref,
+                                         const float* __restrict__ mtag, float* __restrict__ out, int N, int h, int w,
+                                         int C, int MH, int MW) {
+    const int n = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int row = threadIdx.x >> 5;  // 8 rows of threads stride over pixels
+    const int sh = MH / h, sw = MW / w;
+    __shared__ float red[8][33];
+    __shared__ float cnt_s[8];
+    float acc = 0.f, cnt = 0.f;
+    for (int pidx = row; pidx < h * w; pidx += 8) {
+        const int ph = pidx / w, pw = pidx - ph * w;
+        const float m = mref[((size_t)n * MH + (size_t)ph * sh) * MW + (size_t)pw * sw];
+        cnt += m;
+        if (c < C) acc += x[(((size_t)n * h + ph) * w + pw) * C + c] * m;
+    }
+    red[row][threadIdx.x & 31] = acc;
+    if ((threadIdx.x & 31) == 0) cnt_s[row] = cnt;
+    __syncthreads();
+    float tot = 0.f, ctot = 0.f;
+    for (int r = 0; r < 8; ++r) { tot += red[r][threadIdx.x & 31]; ctot += cnt_s[r]; }
+    const float mean = tot / fmaxf(ctot, 1.f);
+    for (int pidx = row; pidx < h * w; pidx += 8) {
+        const int ph = pidx / w, pw = pidx - ph * w;
+        const float m = mtag[((size_t)n * MH + (size_t)ph * sh) * MW + (size_t)pw * sw];
+        if (c < C) out[(((size_t)n * h + ph) * w + pw) * C + c] = mean * m;
+    }
+}
+
+// F.interpolate(mode='bilinear', align_corners=False) on NHWC (encoder.py:222-223)
+__global__ void resize_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C,
+                                       int OH, int OW) {
+    const long long total = (long long)N * OH * OW * C;
+    const float sh = (float)H / OH, sw = (float)W / OW;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = idx % C;
+        long long t = idx / C;
+        const int ow = t % OW; t /= OW;
+        const int oh = t % OH;
+        const int n = t / OH;
+        float fy = ((float)oh + 0.5f) * sh - 0.5f; if (fy < 0.f) fy = 0.f;
+        float fx = ((float)ow + 0.5f) * sw - 0.5f; if (fx < 0.f) fx = 0.f;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly = fy - y0, lx = fx - x0;
+        const float* b = in + (size_t)n * H * W * C + c;
+        const float v00 = b[((size_t)y0 * W + x0) * C], v01 = b[((size_t)y0 * W + x1) * C];
+        const float v10 = b[((size_t)y1 * W + x0) * C], v11 = b[((size_t)y1 * W + x1) * C];
+        out[idx] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    }
+}
+
+// ReflectionPad2d(p) on NHWC, optional TF32 rounding (MaskGAN_networks.py:120-121,168)
+__global__ void reflect_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C, int p,
+                                   int round_) {
+    const int G = C / 4;
+    const int PH = H + 2 * p, PW = W + 2 * p;
+    const long long total = (long long)N * PH * PW * G;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = idx % G;
+        long long t = idx / G;
+        const int pw = t % PW; t /= PW;
+        const int ph = t % PH;
+        const int n = t / PH;
+        int ih = ph - p, iw = pw - p;
+        if (ih < 0) ih = -ih;
+        if (ih >= H) ih = 2 * H - 2 - ih;
+        if (iw < 0) iw = -iw;
+        if (iw >= W) iw = 2 * W - 2 - iw;
+        float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)n * H + ih) * W + iw) * C) + g);
+        if (round_) { v.x = rtf32(v.x); v.y = rtf32(v.y); v.z = rtf32(v.z); v.w = rtf32(v.w); }
+        reinterpret_cast<float4*>(out)[idx] = v;
     }
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, long long HW,
@@ -701,9 +808,10 @@ extern "C" int mg_prep_bginput(const float* img, const float* noise, const float
     prep_bginput_kernel<<<ew_grid((long long)N * H * W), 256, 0, ST(stream)>>>(img, noise, back, out4, N, (long long)H * W);
     return check_launch("mg_prep_bginput");
 }
-extern "C" int mg_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, int CP, void* stream) {
+extern "C" int mg_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, int CP, const float* pmul,
+                               void* stream) {
     if (!in || !out) return set_error(-1, "mg_nchw_to_nhwc: null pointer");
-    nchw_to_nhwc_kernel<<<ew_grid((long long)N * H * W * CP), 256, 0, ST(stream)>>>(in, out, N, C, (long long)H * W, CP);
+    nchw_to_nhwc_kernel<<<ew_grid((long long)N * H * W * CP), 256, 0, ST(stream)>>>(in, out, N, C, (long long)H * W, CP, pmul);
     return check_launch("mg_nchw_to_nhwc");
 }
 extern "C" int mg_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, int CP, void* stream) {
@@ -726,4 +834,125 @@ extern "C" int mg_avgpool3s2(const float* in, float* out, int N, int H, int W, i
     if (C % 4 != 0) return set_error(-2, "mg_avgpool3s2: C%%4");
     avgpool3s2_kernel<<<ew_grid((long long)N * OH * OW * (C / 4)), 256, 0, ST(stream)>>>(in, out, N, H, W, C, OH, OW);
     return check_launch("mg_avgpool3s2");
+}
+
+extern "C" int mg_partial_mask(const float* mask, float* ratio, float* update, int N, int H, int W, int k, int stride,
+                               int pad, void* stream) {
+    if (!mask || !ratio || !update) return set_error(-1, "mg_partial_mask: null pointer");
+    const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    partial_mask_kernel<<<ew_grid((long long)N * OH * OW), 256, 0, ST(stream)>>>(mask, ratio, update, N, H, W, OH, OW, k,
+                                                                               stride, pad);
+    return check_launch("mg_partial_mask");
+}
+extern "C" int mg_masked_mean_bcast(const float* x, const float* mref, const float* mtag, float* out, int N, int h, int w,
+                                    int C, int MH, int MW, void* stream) {
+    if (!x || !mref || !mtag || !out) return set_error(-1, "mg_masked_mean_bcast: null pointer");
+    if (MH % h != 0 || MW % w != 0) return set_error(-2, "mg_masked_mean_bcast: mask size must be a multiple of the map size");
+    dim3 grid(cdiv(C, 32), N);
+    masked_mean_bcast_kernel<<<grid, 256, 0, ST(stream)>>>(x, mref, mtag, out, N, h, w, C, MH, MW);
+    return check_launch("mg_masked_mean_bcast");
+}
+extern "C" int mg_resize_bilinear(const float* in, float* out, int N, int H, int W, int C, int OH, int OW, void* stream) {
+    if (!in || !out) return set_error(-1, "mg_resize_bilinear: null pointer");
+    resize_bilinear_kernel<<<ew_grid((long long)N * OH * OW * C), 256, 0, ST(stream)>>>(in, out, N, H, W, C, OH, OW);
+    return check_launch("mg_resize_bilinear");
+}
+extern "C" int mg_reflect_pad(const float* in, float* out, int N, int H, int W, int C, int pad, int round_tf32,
+                              void* stream) {
+    if (!in || !out) return set_error(-1, "mg_reflect_pad: null pointer");
+    if (C % 4 != 0 || pad >= H || pad >= W) return set_error(-2, "mg_reflect_pad: C%%4==0 and pad < size required");
+    reflect_pad_kernel<<<ew_grid((long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 4)), 256, 0, ST(stream)>>>(
+        in, out, N, H, W, C, pad, round_tf32);
+    return check_launch("mg_reflect_pad");
+}
+
+// ------------------------------------------------------------------------------------ spectral norm (batched)
+// torch SpectralNorm.compute_weight for every spectrally-normalised conv of a network in 3 launches
+// (architecture.py:38-42, normalization.py:28-29): training -> v = normalize(W^T u), u = normalize(W v)
+// in place; always sigma = u^T W v and inv_sigma = 1/sigma (consumed by mg_pack_weight).
+namespace mg {
+struct SnDesc {
+    const float* w;   // [O][K]
+    float* u;         // [O]
+    float* v;         // [K]
+    float* t;         // [K] workspace (zeroed by the caller)
+    float* s;         // [O] workspace
+    float* inv_sigma; // [1]
+    int O, K;
+};
+
+__global__ void __launch_bounds__(128) sn_wtu_kernel(const SnDesc* __restrict__ descs, int row_splits) {
+    const SnDesc d = descs[blockIdx.y];
+    const int chunk = blockIdx.x / row_splits, split = blockIdx.x % row_splits;
+    const int k = chunk * 128 + threadIdx.x;
+    if (chunk * 128 >= d.K) return;
+    const int rows_per = (d.O + row_splits - 1) / row_splits;
+    const int r0 = split * rows_per, r1 = min(d.O, r0 + rows_per);
+    if (k < d.K) {
+        float acc = 0.f;
+        for (int o = r0; o < r1; ++o) acc = fmaf(__ldg(d.w + (size_t)o * d.K + k), __ldg(d.u + o), acc);
+        atomicAdd(d.t + k, acc);
+    }
+}
+__global__ void __launch_bounds__(256) sn_wv_kernel(const SnDesc* __restrict__ descs, int training) {
+    const SnDesc d = descs[blockIdx.y];
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (o >= d.O) return;
+    const int lane = threadIdx.x & 31;
+    const float* vec = training ? d.t : d.v;
+    const float* wr = d.w + (size_t)o * d.K;
+    float acc = 0.f;
+    for (int k = lane; k < d.K; k += 32) acc = fmaf(__ldg(wr + k), vec[k], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) d.s[o] = acc;
+}
+__device__ float block_sum_256(float v, float* sh) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < 8; ++i) r += sh[i];
+    return r;
+}
+__global__ void __launch_bounds__(256) sn_finish_kernel(const SnDesc* __restrict__ descs, int training, float eps) {
+    const SnDesc d = descs[blockIdx.x];
+    __shared__ float sh[8];
+    if (training) {
+        float a = 0.f;
+        for (int k = threadIdx.x; k < d.K; k += 256) a = fmaf(d.t[k], d.t[k], a);
+        const float nt = fmaxf(sqrtf(block_sum_256(a, sh)), eps);
+        float b = 0.f;
+        for (int o = threadIdx.x; o < d.O; o += 256) { const float wv = d.s[o] / nt; b = fmaf(wv, wv, b); }
+        const float n2 = block_sum_256(b, sh);
+        const float nu = fmaxf(sqrtf(n2), eps);
+        for (int k = threadIdx.x; k < d.K; k += 256) { d.v[k] = d.t[k] / nt; d.t[k] = 0.f; }
+        for (int o = threadIdx.x; o < d.O; o += 256) d.u[o] = d.s[o] / nt / nu;
+        if (threadIdx.x == 0) d.inv_sigma[0] = nu / n2;  // sigma = u.(Wv) = |Wv|^2 / nu
+    } else {
+        float a = 0.f;
+        for (int o = threadIdx.x; o < d.O; o += 256) a = fmaf(d.u[o], d.s[o], a);
+        const float sigma = block_sum_256(a, sh);
+        if (threadIdx.x == 0) d.inv_sigma[0] = 1.f / sigma;
+    }
+}
+}  // namespace mg
+
+extern "C" int mg_spectral_norm_batched(const void* descs, int n_layers, int max_O, int max_K, int training, float eps,
+                                        void* stream) {
+    if (!descs || n_layers <= 0) return set_error(-1, "mg_spectral_norm_batched: bad arguments");
+    const SnDesc* d = reinterpret_cast<const SnDesc*>(descs);
+    if (training) {
+        const int splits = 8;
+        dim3 g((unsigned)(cdiv(max_K, 128) * splits), (unsigned)n_layers);
+        sn_wtu_kernel<<<g, 128, 0, ST(stream)>>>(d, splits);
+        count_launch();
+    }
+    dim3 g2((unsigned)cdiv(max_O, 8), (unsigned)n_layers);
+    sn_wv_kernel<<<g2, 256, 0, ST(stream)>>>(d, training);
+    count_launch();
+    sn_finish_kernel<<<n_layers, 256, 0, ST(stream)>>>(d, training, eps);
+    return check_launch("mg_spectral_norm_batched");
 }

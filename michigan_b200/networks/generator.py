@@ -1,0 +1,122 @@
+"""SPADEBGenerator (`--netG spadeb`) — constructor, forward signature and state-dict layout of the
+reference's models/networks/generator.py:19-230; the forward runs on the sm_100a kernels.
+
+Data layout: every internal activation is NHWC fp32 in HBM; tensors that feed a tensor-core conv are
+written TF32-rounded by their producer; the 2x nearest upsamples (generator.py:72,163-210) and the
+hair/background mask pyramids (generator.py:149-159, encoder.py:332-336) are never materialised -
+consumers index the low-resolution tensor / full-resolution mask directly.
+"""
+import torch
+
+from .. import ops
+from .architecture import SPADEResnetBlock
+from .base_network import BaseNetwork
+from .encoder import BackgroundEncode2, ImageEncoder3
+from .prep import PackCache, SpectralNormBatch
+
+
+class SPADEBGenerator(BaseNetwork):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        parser.set_defaults(norm_G="spectralspadesyncbatch3x3")
+        return parser
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        nf = opt.ngf
+        self.sw, self.sh = self.compute_latent_vector_size(opt)
+        if getattr(opt, "use_vae", False) or not opt.use_encoder or opt.Image_encoder_mode != "partialconv":
+            raise NotImplementedError("michigan_b200: spadeb is implemented for --use_encoder with the partialconv "
+                                      "reference encoder (the README configuration)")
+        if not opt.noise_background:
+            raise NotImplementedError("michigan_b200: spadeb is implemented for --noise_background (BackgroundEncode2)")
+        if opt.num_upsampling_layers != "more":
+            raise NotImplementedError("michigan_b200: num_upsampling_layers must be 'more' (the default)")
+        if getattr(opt, "no_orientation", False):
+            raise NotImplementedError("michigan_b200: the orientation map is required")
+        self.fc = ImageEncoder3(opt, self.sw, self.sh)
+        self.head_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.G_middle_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.G_middle_1 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.up_0 = SPADEResnetBlock(16 * nf, 8 * nf, opt)
+        self.up_1 = SPADEResnetBlock(8 * nf, 4 * nf, opt)
+        self.up_2 = SPADEResnetBlock(4 * nf, 2 * nf, opt)
+        self.up_3 = SPADEResnetBlock(2 * nf, 1 * nf, opt)
+        final_nc = nf
+        self.conv_img = torch.nn.Conv2d(final_nc, 3, 3, padding=1)
+        self.up = torch.nn.Upsample(scale_factor=2)
+        self.backgroud_enc = BackgroundEncode2(opt)  # (sic) the reference's attribute name
+        self._blocks = ["head_0", "G_middle_0", "G_middle_1", "up_0", "up_1", "up_2", "up_3"]
+        self._snb = None
+        self.last_taps = None
+        self.collect_taps = False
+
+    def compute_latent_vector_size(self, opt):
+        n_up = {"normal": 5, "more": 6, "most": 7}.get(opt.num_upsampling_layers)
+        if n_up is None:
+            raise ValueError("opt.num_upsampling_layers [%s] not recognized" % opt.num_upsampling_layers)
+        if opt.add_feat_zeros:
+            sw = (opt.crop_size + opt.add_th) // (2 ** n_up)
+        else:
+            sw = opt.crop_size // (2 ** n_up)
+        sh = round(sw / opt.aspect_ratio)
+        return sw, sh
+
+    def spectral_batch(self):
+        if self._snb is None:
+            convs = []
+            for b in self._blocks:
+                convs += getattr(self, b).sn_convs()
+            self._snb = SpectralNormBatch(convs)
+        return self._snb
+
+    def forward(self, input=None, z=None, orient_mask=None, image_ref=None, input_tag=None, noise=None, image_tag=None):
+        """generator.py:107-230.  All arguments NCHW CUDA tensors; returns the [N,3,H,W] image in [-1,1]."""
+        opt = self.opt
+        if getattr(opt, "orient_random_disturb", False) or getattr(opt, "use_clip", False):
+            raise NotImplementedError("michigan_b200: orient_random_disturb / use_clip are debugging paths")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd import generator_forward_autograd
+            return generator_forward_autograd(self, input, orient_mask, image_ref, input_tag, noise, image_tag)
+        return self.forward_nograd(input, orient_mask, image_ref, input_tag, noise, image_tag)
+
+    def forward_nograd(self, input, orient_mask, image_ref, input_tag, noise, image_tag):
+        opt = self.opt
+        N, _, H, W = input_tag.shape
+        input_tag = input_tag.contiguous()
+        seg4 = ops.prep_seg(input_tag, orient_mask.contiguous())          # generator.py:129-142
+        ins_ref = input[:, 1:2]
+        ins_tag = input_tag[:, 1:2]
+        x = self.fc.forward_nhwc(image_ref, ins_ref, ins_tag)              # generator.py:117-123
+        feats, back = self.backgroud_enc.forward_nhwc(image_tag, input_tag, noise)  # generator.py:144-147
+        hair = input_tag[:, 1].contiguous()
+        snb = self.spectral_batch()
+        inv = snb.run(self.training)
+        inv_of = {c: inv[i:i + 1] for i, c in enumerate(snb.convs)}
+        taps = {} if self.collect_taps else None
+        if taps is not None:
+            taps["fc"] = x
+            for i, f in enumerate(feats):
+                taps["bg%d" % i] = f
+
+        x = self.head_0.forward_nhwc(x, 0, seg4, inv_of)
+        if taps is not None:
+            taps["head_0"] = x
+        x = self.G_middle_0.forward_nhwc(x, 1, seg4, inv_of)
+        if taps is not None:
+            taps["G_middle_0"] = x
+        x = self.G_middle_1.forward_nhwc(x, 1, seg4, inv_of)
+        if taps is not None:
+            taps["G_middle_1"] = x
+        for i in range(4):
+            blk = getattr(self, "up_%d" % i)
+            ms = 8 >> i  # hair_masks / back_masks pyramid level == stride into the full-resolution masks
+            if opt.bf_direct_add:
+                raise NotImplementedError("michigan_b200: --bf_direct_add is not implemented")
+            x = blk.forward_nhwc(x, 1, seg4, inv_of, blend=(feats[i], hair, back, ms))
+            if taps is not None:
+                taps["up_%d" % i] = x
+        out = ops.conv_img(x, self.conv_img.weight.detach(), self.conv_img.bias.detach())  # generator.py:227-228
+        self.last_taps = taps
+        return out

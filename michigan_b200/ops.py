@@ -238,12 +238,48 @@ def prep_bginput(img_nchw, noise_nchw, back):
     return out
 
 
-def nchw_to_nhwc(x, cpad=None):
-    _chk(x, "x")
+def nchw_to_nhwc(x, cpad=None, pmul=None):
+    _chk(x, "x"); _chk(pmul, "pmul")
     N, Cc, H, W = x.shape
     cp = cpad or Cc
     out = torch.empty((N, H, W, cp), device=x.device, dtype=torch.float32)
-    check(_lib.load().mg_nchw_to_nhwc(_p(x), _p(out), N, Cc, H, W, cp, _stream()), "mg_nchw_to_nhwc")
+    check(_lib.load().mg_nchw_to_nhwc(_p(x), _p(out), N, Cc, H, W, cp, _p(pmul), _stream()), "mg_nchw_to_nhwc")
+    return out
+
+
+def partial_mask(mask, k, stride, pad):
+    """PartialConv2d mask update: mask [N,H,W] -> (mask_ratio, update_mask) [N,OH,OW]."""
+    _chk(mask, "mask")
+    N, H, W = mask.shape
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    ratio = torch.empty((N, OH, OW), device=mask.device, dtype=torch.float32)
+    upd = torch.empty_like(ratio)
+    check(_lib.load().mg_partial_mask(_p(mask), _p(ratio), _p(upd), N, H, W, k, stride, pad, _stream()), "mg_partial_mask")
+    return ratio, upd
+
+
+def masked_mean_bcast(x, mref, mtag):
+    _chk(x, "x"); _chk(mref, "mref"); _chk(mtag, "mtag")
+    N, h, w, Cc = x.shape
+    out = torch.empty_like(x)
+    check(_lib.load().mg_masked_mean_bcast(_p(x), _p(mref), _p(mtag), _p(out), N, h, w, Cc, mref.shape[-2],
+                                           mref.shape[-1], _stream()), "mg_masked_mean_bcast")
+    return out
+
+
+def resize_bilinear(x, oh, ow):
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, oh, ow, Cc), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_resize_bilinear(_p(x), _p(out), N, H, W, Cc, oh, ow, _stream()), "mg_resize_bilinear")
+    return out
+
+
+def reflect_pad(x, pad, round_tf32=False):
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, H + 2 * pad, W + 2 * pad, Cc), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_reflect_pad(_p(x), _p(out), N, H, W, Cc, pad, int(round_tf32), _stream()), "mg_reflect_pad")
     return out
 
 

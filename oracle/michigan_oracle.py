@@ -275,6 +275,8 @@ def generator_forward(sd, opt, input_ref, input_tag, image_ref, image_tag, orien
         taps["G_middle_1"] = x
     for i in range(4):
         x = spade_resnet_block(up(x), seg, sd, "up_%d" % i, training, **bn_kw)
+        if taps is not None:
+            taps["up_%d_pre" % i] = x
         if opt.bf_direct_add:
             x = back_feats[i] + x
         else:

@@ -1,0 +1,160 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden
+fixtures.  Tolerances: tensor-core convs read TF32 operands (10-bit mantissa, RN-rounded by the
+producer) with fp32 accumulation, so feature maps are compared at 5e-3 of their abs-max and the
+generator image against BASELINE.json's bound: max-abs <= 1e-3 (mean-abs reported, must be <= 2e-4)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import michigan_oracle as orc
+from helpers import assert_summary_close, load_golden, max_mean_abs, preprocessed, reference_layout_state
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 1e-3
+MEAN_ABS = 2e-4
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def _build_G(cfg, is_train, sd=None, **kw):
+    from michigan_b200 import networks
+    from michigan_b200.options import make_opt
+    opt = make_opt(is_train=is_train, ngf=cfg["ngf"], ndf=cfg["ndf"], crop_size=cfg["size"], **kw)
+    G = networks.SPADEBGenerator(opt)
+    if sd is not None:
+        missing = G.load_state_dict(sd, strict=True)
+    return G.cuda(), opt
+
+
+def _run_G(G, pre):
+    p = _cuda(pre)
+    with torch.no_grad():
+        return G(p["input_ref"], orient_mask=p["orient_mask"], image_ref=p["image_ref"], input_tag=p["input_tag"],
+                 noise=p["noise"], image_tag=p["image_tag"])
+
+
+def test_generator_train_mode_vs_golden_and_oracle():
+    z, cfg = load_golden()
+    sd = reference_layout_state("G", cfg, cfg["seed_G"])
+    G, opt = _build_G(cfg, True, sd)
+    G.train()
+    G.collect_taps = True
+    _, pre = preprocessed(cfg)
+    random.seed(cfg["py_seed"])  # the reference draws the dilation size with Python's `random` (encoder.py:294)
+    out = _run_G(G, pre)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(z["g_train_out"])
+    mx, mn = max_mean_abs(out, ref)
+    print("G train-mode vs reference fixture: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    for name, t in G.last_taps.items():
+        rel = assert_summary_close("tap " + name, t.permute(0, 3, 1, 2).contiguous(), z["tap/" + name], 5e-3)
+        print("   tap %-12s rel err %.2e" % (name, rel))
+    assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
+    # side effects of a train-mode forward: running statistics and spectral-norm u, v
+    got = G.state_dict()
+    for k in z.files:
+        if k.startswith("g_post/"):
+            name = k[len("g_post/"):]
+            r = torch.from_numpy(z[k])
+            tol = 2e-3 if name.endswith(("running_mean", "running_var")) else 1e-4
+            err = (got[name].cpu() - r).abs().max().item()
+            assert err <= tol * max(1.0, r.abs().max().item()), (name, err)
+    assert all(int(v) == 0 for k, v in got.items() if k.endswith("num_batches_tracked"))
+
+
+def test_generator_eval_mode_vs_golden():
+    z, cfg = load_golden()
+    sd = reference_layout_state("G", cfg, cfg["seed_G"])
+    for k in z.files:
+        if k.startswith("g_post/"):
+            sd[k[len("g_post/"):]] = torch.from_numpy(z[k]).clone()
+    G, opt = _build_G(cfg, False, sd)
+    G.eval()
+    before = {k: v.clone() for k, v in G.state_dict().items()}
+    _, pre = preprocessed(cfg)
+    out = _run_G(G, pre)
+    mx, mn = max_mean_abs(out, torch.from_numpy(z["g_eval_out"]))
+    print("G eval-mode vs reference fixture: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
+    after = G.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before), "eval forward must not modify state"
+    # determinism: same inputs, same bits
+    assert torch.equal(out, _run_G(G, pre))
+
+
+def test_discriminator_vs_golden():
+    from michigan_b200 import networks
+    from michigan_b200.options import make_opt
+    z, cfg = load_golden()
+    sd = reference_layout_state("D", cfg, cfg["seed_D"])
+    oopt = orc.default_opt(ngf=cfg["ngf"], ndf=cfg["ndf"], crop_size=cfg["size"])
+    _, pre = preprocessed(cfg)
+    fake = torch.from_numpy(z["g_train_out"])
+    o = orc.orient_channels(pre["orient_mask"], pre["input_tag"][:, 1:2], oopt)
+    x = torch.cat([torch.cat([pre["input_tag"], o, fake], 1), torch.cat([pre["input_tag"], o, pre["image_tag"]], 1)], 0)
+    D = networks.MultiscaleDiscriminator(make_opt(ngf=cfg["ngf"], ndf=cfg["ndf"], crop_size=cfg["size"]))
+    D.load_state_dict(sd, strict=True)
+    D = D.cuda().train()
+    with torch.no_grad():
+        out = D(x.cuda())
+    assert len(out) == 2 and all(len(o_) == 5 for o_ in out)
+    for i in range(2):
+        for j in range(5):
+            t = out[i][j]
+            assert t.shape[1] == (1 if j == 4 else min(cfg["ndf"] * 2 ** j, 512))
+            if j == 4:
+                r = torch.from_numpy(z["d/%d/4" % i])
+                mx, mn = max_mean_abs(t, r)
+                print("D[%d] logits max-abs %.3e (ref max %.2f)" % (i, mx, r.abs().max()))
+                assert mx <= 5e-3 * r.abs().max().item()
+            else:
+                assert_summary_close("D[%d][%d]" % (i, j), t.contiguous(), z["d/%d/%d" % (i, j)], 5e-3)
+    got = D.state_dict()
+    for k in z.files:
+        if k.startswith("d_post/"):
+            r = torch.from_numpy(z[k])
+            assert (got[k[len("d_post/"):]].cpu() - r).abs().max().item() <= 1e-4
+
+
+def test_generator_full_size_vs_oracle():
+    """BASELINE config shape (ngf 64, 512x512) at batch 1 against the oracle run on the host CPU."""
+    cfg = dict(ngf=64, ndf=64, size=512, batch=1, data_seed=3)
+    sd = reference_layout_state("G", cfg, 21)
+    G, opt = _build_G(cfg, True, sd)
+    G.train()
+    _, pre = preprocessed(cfg)
+    random.seed(9)
+    th = int(512 * 0.05); th = th if th % 2 == 1 else th + 1
+    k = random.choice([max(th - 4, 1), max(th - 2, 1), th, th + 2, th + 4])
+    random.seed(9)
+    out = _run_G(G, pre)
+    oopt = orc.default_opt(isTrain=True)
+    with torch.no_grad():
+        ref = orc.generate_fake(sd, oopt, pre, True, rng_k=k)
+    mx, mn = max_mean_abs(out, ref)
+    print("G 512x512 ngf64 vs oracle: max-abs %.3e mean-abs %.3e (output std %.3f)" % (mx, mn, ref.std().item()))
+    assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
+
+
+def test_eval_batch_independence_at_benchmark_size():
+    """Size-independent property at the BASELINE batch (N=8, 512x512): in eval mode every op is
+    per-sample, so the batched result equals the per-image results bit for bit."""
+    cfg = dict(ngf=64, ndf=64, size=512, batch=8, data_seed=5)
+    sd = reference_layout_state("G", cfg, 22)
+    G, opt = _build_G(cfg, False, sd)
+    G.eval()
+    data, pre = preprocessed(cfg)
+    # different image per sample so that samples are distinguishable
+    g = torch.Generator().manual_seed(1)
+    pre["image_ref"] = torch.rand(8, 3, 512, 512, generator=g) * 2 - 1
+    pre["image_tag"] = pre["image_ref"].clone()
+    out = _run_G(G, pre)
+    for i in (0, 5):
+        one = {k: v[i:i + 1].contiguous() for k, v in pre.items()}
+        assert torch.equal(out[i:i + 1], _run_G(G, one)), "sample %d differs between batched and single run" % i
+    assert torch.isfinite(out).all() and out.abs().max() <= 1.0
