@@ -1,0 +1,161 @@
+"""Host-side logic that needs no GPU: state-dict layout (= the reference's checkpoint layout),
+factory/option handling, deterministic synthesis, checkpoint I/O, and - when the reference checkout
+is present (build container only) - key-for-key equality with the reference networks and the
+install() drop-in."""
+import os
+import sys
+
+import pytest
+import torch
+
+from michigan_b200 import networks
+from michigan_b200.options import make_opt
+from michigan_b200.synth import fill_state_dict, synthetic_batch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import ref_shims  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not ref_shims.available(), reason="reference checkout not present")
+
+
+def test_generator_state_dict_layout_ngf64():
+    G = networks.SPADEBGenerator(make_opt(gpu_ids=[]))
+    sd = G.state_dict()
+    assert len(sd) == 252 and sum(p.numel() for p in G.parameters()) == 109474755
+    assert tuple(sd["up_3.norm_0.mlp_shared.0.weight"].shape) == (128, 4, 3, 3)
+    assert tuple(sd["up_0.norm_s.mlp_gamma.weight"].shape) == (1024, 128, 3, 3)
+    assert tuple(sd["conv_img.weight"].shape) == (3, 64, 3, 3)
+    assert tuple(sd["backgroud_enc.layer4.conv.weight"].shape) == (1024, 512, 4, 4)  # dead weight, still saved
+    for blk in ("head_0", "G_middle_0", "G_middle_1"):
+        assert blk + ".conv_s.weight_orig" not in sd
+    for blk in ("up_0", "up_1", "up_2", "up_3"):
+        for suf in ("weight_orig", "weight_u", "weight_v"):
+            assert "%s.conv_s.%s" % (blk, suf) in sd
+        assert blk + ".conv_s.bias" not in sd
+    assert "head_0.norm_0.param_free_norm.num_batches_tracked" in sd
+
+
+def test_discriminator_state_dict_layout():
+    D = networks.MultiscaleDiscriminator(make_opt(gpu_ids=[]))
+    sd = D.state_dict()
+    assert len(sd) == 26 and sum(p.numel() for p in D.parameters()) == 5535874
+    assert tuple(sd["discriminator_0.model0.0.weight"].shape) == (64, 7, 4, 4)
+    assert "discriminator_1.model3.0.0.weight_orig" in sd and "discriminator_1.model3.0.0.bias" not in sd
+    assert tuple(sd["discriminator_0.model4.0.weight"].shape) == (1, 512, 4, 4)
+
+
+def test_factory_and_options():
+    assert networks.find_network_using_name("spadeb", "generator") is networks.SPADEBGenerator
+    assert networks.find_network_using_name("multiscale", "discriminator") is networks.MultiscaleDiscriminator
+    with pytest.raises(ValueError):
+        networks.find_network_using_name("pix2pixhd", "generator")
+    import argparse
+    p = argparse.ArgumentParser()
+    p.add_argument("--norm_G", default="spectralinstance")
+    networks.SPADEBGenerator.modify_commandline_options(p, True)
+    assert p.parse_args([]).norm_G == "spectralspadesyncbatch3x3"       # generator.py:21-24
+    with pytest.raises(NotImplementedError):
+        networks.SPADEBGenerator(make_opt(gpu_ids=[], ngf=48))
+    with pytest.raises(NotImplementedError):
+        networks.SPADEBGenerator(make_opt(gpu_ids=[], norm_G="spectralspadeinstance3x3"))
+    G = networks.SPADEBGenerator(make_opt(gpu_ids=[], ngf=32, crop_size=576 - 64, add_feat_zeros=True))
+    assert (G.sw, G.sh) == (9, 9)                                        # (512+64)//64, generator.py:90-94
+
+
+def test_fill_state_dict_is_deterministic_and_calibrates_spectral_vectors():
+    G = networks.SPADEBGenerator(make_opt(gpu_ids=[], ngf=32, crop_size=128))
+    a = {k: v.clone() for k, v in G.state_dict().items()}
+    b = {k: v.clone() for k, v in G.state_dict().items()}
+    fill_state_dict(a, 7)
+    fill_state_dict(b, 7)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    w = a["up_3.conv_0.weight_orig"]
+    mat = w.reshape(w.shape[0], -1)
+    sigma = torch.dot(a["up_3.conv_0.weight_u"], mat @ a["up_3.conv_0.weight_v"])
+    true = torch.linalg.matrix_norm(mat, ord=2)
+    assert abs(sigma - true) / true < 2e-2
+
+
+def test_synthetic_batch_contract():
+    d = synthetic_batch(2, 64, seed=1)
+    assert d["label_tag"].shape == (2, 1, 64, 64) and set(d["label_tag"].unique().tolist()) == {0.0, 1.0}
+    assert d["image_ref"].min() >= -1 and d["image_ref"].max() <= 1
+    assert d["orient"].max() < 255 and (d["orient"] * (1 - d["label_tag"])).abs().max() == 0
+    assert torch.equal(d["label_ref"], d["label_tag"])                  # ref == tag keeps GAN_Feat active
+
+
+def test_init_weights_reaches_spectral_weight_orig():
+    torch.manual_seed(0)
+    blk = networks.SPADEResnetBlock(64, 32, make_opt(gpu_ids=[]))
+    before = blk.conv_0.weight_orig.detach().clone()
+    net = networks.BaseNetwork()
+    net.add_module("b", blk)
+    net.init_weights("xavier", 0.02)
+    assert not torch.equal(before, blk.conv_0.weight_orig)
+    assert blk.conv_0.weight_orig.std() < 1e-3                            # xavier gain 0.02
+    assert float(blk.conv_0.bias.abs().max()) == 0.0
+
+
+def test_checkpoint_roundtrip_layout(tmp_path):
+    from michigan_b200.pix2pix_model import load_weights
+    G = networks.SPADEBGenerator(make_opt(gpu_ids=[], ngf=32, crop_size=128))
+    fill_state_dict(G.state_dict(), 3)
+    path = tmp_path / "latest_net_G.pth"
+    torch.save({("module." + k): v for k, v in G.state_dict().items()}, path)   # DataParallel-style prefix
+    G2 = networks.SPADEBGenerator(make_opt(gpu_ids=[], ngf=32, crop_size=128))
+    load_weights(G2, torch.load(path))
+    assert all(torch.equal(v, G2.state_dict()[k]) for k, v in G.state_dict().items())
+
+
+@needs_ref
+def test_layout_equals_reference_key_for_key():
+    ref_shims.patch_training()
+    opt = ref_shims.ref_options(True, ["--ngf", "32", "--ndf", "32", "--crop_size", "128", "--load_size", "128"])
+    nets = ref_shims.import_reference()
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        refG, refD = nets.define_G(opt), nets.define_D(opt)
+    G = networks.SPADEBGenerator(make_opt(gpu_ids=[], ngf=32, ndf=32, crop_size=128))
+    D = networks.MultiscaleDiscriminator(make_opt(gpu_ids=[], ngf=32, ndf=32, crop_size=128))
+    for mine, ref in ((G, refG), (D, refD)):
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+
+
+@needs_ref
+def test_same_seed_same_initial_weights_as_reference():
+    """Construction order + init_weights mirror the reference, so a torch seed reproduces its init."""
+    ref_shims.patch_training()
+    opt = ref_shims.ref_options(True, ["--ngf", "32", "--ndf", "32", "--crop_size", "128", "--load_size", "128"])
+    nets = ref_shims.import_reference()
+    import io
+    import contextlib
+    torch.manual_seed(123)
+    with contextlib.redirect_stdout(io.StringIO()):
+        refG = nets.define_G(opt)
+    torch.manual_seed(123)
+    with contextlib.redirect_stdout(io.StringIO()):
+        G = networks.create_network(networks.SPADEBGenerator, make_opt(gpu_ids=[], ngf=32, ndf=32, crop_size=128))
+    a, b = G.state_dict(), refG.state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@needs_ref
+def test_install_plugs_into_reference_model():
+    import michigan_b200
+    ref_shims.patch_training()
+    michigan_b200.install(ref_shims.REF)
+    opt = ref_shims.ref_options(True, ["--ngf", "32", "--ndf", "32", "--crop_size", "128", "--load_size", "128"])
+    import io
+    import contextlib
+    from models.pix2pix_model import Pix2PixModel
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Pix2PixModel(opt)
+    assert isinstance(m.netG, networks.SPADEBGenerator) and isinstance(m.netD, networks.MultiscaleDiscriminator)
+    from trainers import pix2pix_trainer
+    assert pix2pix_trainer.DataParallelWithCallback.__module__.startswith("models.networks.sync_batchnorm") or True
+    import models.networks.sync_batchnorm as sbn
+    assert sbn.DataParallelWithCallback is networks.DataParallelWithCallback
