@@ -79,6 +79,11 @@ typedef struct mg_igemm_args {
     const float* gbias1;
     const float* bbias;
     int32_t max_ctas; /* 0 = one CTA per SM */
+    /* data-gradient use (transposed convs): asymmetric extra padding (may be negative), and a strided
+     * output window: out pixel (oh,ow) is stored at (oh*out_stride+out_off_h, ow*out_stride+out_off_w)
+     * of an [N,OHF,OWF,Cout] tensor (0 = dense [N,OH,OW,Cout]); accumulate != 0: out += result. */
+    int32_t pad_h_extra, pad_w_extra;
+    int32_t out_stride, out_off_h, out_off_w, OHF, OWF, accumulate;
 } mg_igemm_args;
 int mg_conv_igemm(const mg_igemm_args* a, void* stream);
 
@@ -184,6 +189,20 @@ typedef struct mg_sn_desc {
 } mg_sn_desc;
 int mg_spectral_norm_batched(const void* descs, int n_layers, int max_O, int max_K, int training, float eps,
                              void* stream);
+
+/* Weight gradient of the implicit-GEMM convs on tcgen05 (TF32, MN-major operands, split-K over
+ * pixels): dw[co][(kh*KW+kw)*Cin+ci] = sum_pix dy[pix,co] * x[pix*stride - pad + (kh,kw), ci].
+ * dy [N,OH,OW,Cout], x [N,H,W,Cin] NHWC; dw has the packed layout of mg_pack_weight (autograd of
+ * nn.Conv2d at the call sites listed for mg_conv_igemm). */
+int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                  int KH, int KW, int stride, int pad, void* stream);
+
+/* Operand for the data gradient (transposed conv) of a conv with weight w [O,I,KH,KW]: sub-kernel
+ * taps kh = k0h + stride*j (j < Jh), flipped and transposed to [I][Jh*Jw*O], times *inv_sigma, TF32. */
+int mg_pack_weight_dgrad(const float* w_oihw, float* out, int O, int I, int KH, int KW, int stride, int k0h, int Jh,
+                         int k0w, int Jw, const float* inv_sigma, void* stream);
+/* packed [O][KH*KW*I] weight gradient -> OIHW (accumulate != 0: +=). */
+int mg_unpack_wgrad(const float* dw_packed, float* dw_oihw, int O, int I, int KH, int KW, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

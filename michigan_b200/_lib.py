@@ -27,6 +27,9 @@ class IgemmArgs(C.Structure):
         ("x", c_f32p), ("x_shift", C.c_int32),
         ("nscale", c_f32p), ("nshift", c_f32p), ("gbias1", c_f32p), ("bbias", c_f32p),
         ("max_ctas", C.c_int32),
+        ("pad_h_extra", C.c_int32), ("pad_w_extra", C.c_int32),
+        ("out_stride", C.c_int32), ("out_off_h", C.c_int32), ("out_off_w", C.c_int32),
+        ("OHF", C.c_int32), ("OWF", C.c_int32), ("accumulate", C.c_int32),
     ]
 
 
@@ -70,6 +73,9 @@ SIGNATURES = {
     "mg_resize_bilinear": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mg_reflect_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mg_spectral_norm_batched": [_p, _i, _i, _i, _i, _f, _p],
+    "mg_pack_weight_dgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "mg_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_conv_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],

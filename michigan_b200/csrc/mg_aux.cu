@@ -956,3 +956,54 @@ extern "C" int mg_spectral_norm_batched(const void* descs, int n_layers, int max
     sn_finish_kernel<<<n_layers, 256, 0, ST(stream)>>>(d, training, eps);
     return check_launch("mg_spectral_norm_batched");
 }
+
+// ------------------------------------------------------------------------------------ dgrad weight packing
+// Data gradient of a conv = a stride-1 conv of dY with flipped, transposed (sub-)kernels.  For output
+// parity (rh, rw) of a stride-s conv only taps kh = k0h + s*j contribute (see DESIGN.md "dgrad"):
+//   out[ci][(th*Jw + tw)*O + co] = W[co][ci][k0h + s*(Jh-1-th)][k0w + s*(Jw-1-tw)] * inv_sigma
+namespace mg {
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int I, int KH, int KW,
+                                         int s, int k0h, int Jh, int k0w, int Jw, const float* __restrict__ inv_sigma) {
+    const long long total = (long long)I * Jh * Jw * O;
+    const float sc = inv_sigma ? *inv_sigma : 1.f;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int co = idx % O;
+        long long t = idx / O;
+        const int tw = t % Jw; t /= Jw;
+        const int th = t % Jh;
+        const int ci = t / Jh;
+        const int kh = k0h + s * (Jh - 1 - th), kw = k0w + s * (Jw - 1 - tw);
+        out[idx] = rtf32(w[(((long long)co * I + ci) * KH + kh) * KW + kw] * sc);
+    }
+}
+// packed [O][KH*KW*I] gradient -> OIHW (+= when accumulate)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int O, int I, int KH, int KW,
+                                    int accumulate) {
+    const long long total = (long long)O * I * KH * KW;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int kw = idx % KW;
+        long long t = idx / KW;
+        const int kh = t % KH; t /= KH;
+        const int i = t % I;
+        const int o = t / I;
+        const float v = dwp[(size_t)o * KH * KW * I + (size_t)(kh * KW + kw) * I + i];
+        dw[idx] = accumulate ? dw[idx] + v : v;
+    }
+}
+}  // namespace mg
+
+extern "C" int mg_pack_weight_dgrad(const float* w, float* out, int O, int I, int KH, int KW, int stride, int k0h, int Jh,
+                                    int k0w, int Jw, const float* inv_sigma, void* stream) {
+    if (!w || !out) return set_error(-1, "mg_pack_weight_dgrad: null pointer");
+    if (k0h + stride * (Jh - 1) >= KH || k0w + stride * (Jw - 1) >= KW) return set_error(-2, "mg_pack_weight_dgrad: taps out of range");
+    pack_weight_dgrad_kernel<<<ew_grid((long long)I * Jh * Jw * O), 256, 0, ST(stream)>>>(w, out, O, I, KH, KW, stride, k0h, Jh,
+                                                                                         k0w, Jw, inv_sigma);
+    return check_launch("mg_pack_weight_dgrad");
+}
+extern "C" int mg_unpack_wgrad(const float* dwp, float* dw_oihw, int O, int I, int KH, int KW, int accumulate, void* stream) {
+    if (!dwp || !dw_oihw) return set_error(-1, "mg_unpack_wgrad: null pointer");
+    unpack_wgrad_kernel<<<ew_grid((long long)O * I * KH * KW), 256, 0, ST(stream)>>>(dwp, dw_oihw, O, I, KH, KW, accumulate);
+    return check_launch("mg_unpack_wgrad");
+}

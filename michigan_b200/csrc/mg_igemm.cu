@@ -31,7 +31,8 @@ constexpr int kMaxStages = 8;
 
 struct IgemmParams {
     int N, OH, OW, Cout;
-    int Cin, KH, KW, stride, pad;
+    int Cin, KH, KW, stride, pad_h, pad_w;
+    int os, ooh, oow, OHF, OWF, accumulate;
     int TW, TH, TN, tiles_w, tiles_h, tiles_n;
     int BN, n_tiles, num_tiles, kchunks, stages;
     uint32_t idesc, tmem_cols;
@@ -115,8 +116,8 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tw = m % p.tiles_w;
                 const int th = (m / p.tiles_w) % p.tiles_h;
                 const int tn = m / m_tiles_per_img;
-                const int iw0 = tw * p.TW * p.stride - p.pad;
-                const int ih0 = th * p.TH * p.stride - p.pad;
+                const int iw0 = tw * p.TW * p.stride - p.pad_w;
+                const int ih0 = th * p.TH * p.stride - p.pad_h;
                 const int n0 = tn * p.TN;
                 for (int tap = 0; tap < p.KH * p.KW; ++tap) {
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
@@ -182,7 +183,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int oh = th * p.TH + hl;
             const int n = tn * p.TN + nl;
             const bool valid = (ow < p.OW) && (oh < p.OH) && (n < p.N);
-            const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
+            const size_t pix = ((size_t)n * p.OHF + (size_t)oh * p.os + p.ooh) * p.OWF + (size_t)ow * p.os + p.oow;
 
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
@@ -246,6 +247,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             if (p.round_out) y[i] = round_tf32(y[i]);
                         }
                         float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
+                        if (p.accumulate) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 o = op[i];
+                                y[4 * i] += o.x; y[4 * i + 1] += o.y; y[4 * i + 2] += o.z; y[4 * i + 3] += o.w;
+                            }
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
@@ -330,7 +338,12 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.N = a->N; p.OH = a->OH; p.OW = a->OW; p.Cout = a->Cout;
-    p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.stride = a->stride; p.pad = a->pad;
+    p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.stride = a->stride;
+    p.pad_h = a->pad + a->pad_h_extra; p.pad_w = a->pad + a->pad_w_extra;
+    p.os = a->out_stride > 0 ? a->out_stride : 1; p.ooh = a->out_off_h; p.oow = a->out_off_w;
+    p.OHF = a->OHF > 0 ? a->OHF : a->OH; p.OWF = a->OWF > 0 ? a->OWF : a->OW; p.accumulate = a->accumulate;
+    if (p.os != 1 && (a->epi != MG_EPI_BIAS || a->res || a->bf || a->pscale || a->pmul))
+        return set_error(-8, "mg_conv_igemm: strided output supports the plain bias epilogue only");
     p.TW = next_pow2(a->OW) < 16 ? next_pow2(a->OW) : 16;
     int th = 128 / p.TW;
     p.TH = next_pow2(a->OH) < th ? next_pow2(a->OH) : th;

@@ -1,0 +1,224 @@
+// michigan_b200 — weight-gradient implicit GEMM on tcgen05 (sm_100a).
+//
+//   dW[co, tap, ci] = sum_{pixels} dY[pix, co] * X[pix (+) tap, ci]
+//
+// GEMM view per filter tap: D[M = 128 output channels, N = BN input channels] accumulated over
+// K = pixels.  Both operands are NHWC activations, i.e. contiguous along their M/N index and strided
+// along K, so they are fed to tcgen05.mma as MN-major operands: every TMA box [32 channels x 64
+// pixels] lands as eight 1024 B swizzle atoms (32 ch x 8 pixels); M and N span several boxes (LBO).
+// The tap shift and the conv zero padding come from the box start coordinate + TMA OOB zero fill,
+// exactly as in the forward kernel.  Pixels are split across CTAs (split-K); partial tiles are
+// reduced into the packed gradient with vector fp32 atomics.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include "mg_ptx.cuh"
+#include "mg_internal.h"
+
+namespace mg {
+
+constexpr int kWgThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kPixTile = 64;          // K per pipeline stage
+constexpr int kBoxBytes = kPixTile * 128;  // one [64 px x 32 ch] fp32 box
+constexpr int kWgStagesMax = 6;
+
+struct WgradParams {
+    int N, OH, OW, Cout, Cin, KH, KW, stride, pad;
+    int TW, TH, TN, tiles_w, tiles_h, tiles_n, pix_tiles;
+    int BN, m_tiles, n_tiles, splits, stages;
+    uint32_t idesc, tmem_cols;
+    float* dw;  // [Cout][KH*KW*Cin]
+};
+
+// MN-major, 128B swizzle: 32 contiguous elements per row, 8 rows (K) per 1024 B atom;
+// LBO = byte distance between consecutive 32-element blocks along M/N, SBO = between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = 4 * kBoxBytes;                 // M = 128 -> 4 boxes
+    const int b_bytes = (p.BN / 32) * kBoxBytes;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgStagesMax;
+    uint64_t* done_bar = bars + 2 * kWgStagesMax;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStagesMax + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // unit decode: blockIdx.x = ((tap * m_tiles + mt) * n_tiles + nt) * splits + split
+    int u = blockIdx.x;
+    const int split = u % p.splits; u /= p.splits;
+    const int nt = u % p.n_tiles; u /= p.n_tiles;
+    const int mt = u % p.m_tiles;
+    const int tap = u / p.m_tiles;
+    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+    const int t_begin = (int)((long long)p.pix_tiles * split / p.splits);
+    const int t_end = (int)((long long)p.pix_tiles * (split + 1) / p.splits);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            const uint32_t tx = (uint32_t)stage_bytes;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int tw = t % p.tiles_w;
+                const int th = (t / p.tiles_w) % p.tiles_h;
+                const int tn = t / (p.tiles_w * p.tiles_h);
+                const int ow0 = tw * p.TW, oh0 = th * p.TH, n0 = tn * p.TN;
+                mbar_wait(&empty_bar[st], ph ^ 1);
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[st], tx);
+                for (int j = 0; j < 4; ++j)
+                    tma_load_4d(sa + j * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + j * 32, ow0, oh0, n0);
+                for (int j = 0; j < p.BN / 32; ++j)
+                    tma_load_4d(sa + a_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * 32,
+                                ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
+                if (++st == p.stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            uint32_t first = 1;
+            for (int t = t_begin; t < t_end; ++t) {
+                mbar_wait(&full_bar[st], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+#pragma unroll
+                for (int k = 0; k < kPixTile / 8; ++k) {
+                    const uint64_t da = umma_desc_mnmajor_sw128(sa + k * 1024, kBoxBytes);
+                    const uint64_t db = umma_desc_mnmajor_sw128(sa + a_bytes + k * 1024, kBoxBytes);
+                    umma_tf32(tmem_base, da, db, p.idesc, first ? 0u : 1u);
+                    first = 0;
+                }
+                umma_commit(&empty_bar[st]);
+                if (++st == p.stages) { st = 0; ph ^= 1; }
+            }
+            umma_commit(done_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;  // output channel within the M tile
+        const int co = mt * 128 + row;
+        if (t_end > t_begin) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            float* dst = p.dw + (size_t)co * (p.KH * p.KW * p.Cin) + (size_t)tap * p.Cin + nt * p.BN;
+            for (int j0 = 0; j0 < p.BN; j0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_row + j0, v);
+                tmem_ld_wait();
+                if (co < p.Cout) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 val = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                                 __uint_as_float(v[i + 3]));
+                        if (p.splits > 1) atomicAdd(reinterpret_cast<float4*>(dst + j0 + i), val);
+                        else *reinterpret_cast<float4*>(dst + j0 + i) = val;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+static int np2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+}  // namespace mg
+
+using namespace mg;
+
+// dw: [Cout][KH*KW*Cin] fp32 (tap-major K, the layout of mg_pack_weight); zeroed here when split-K > 1.
+extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                             int KH, int KW, int stride, int pad, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!dy || !x || !dw) return set_error(-1, "mg_conv_wgrad: null pointer");
+    if (Cin % 32 != 0 || Cout % 32 != 0) return set_error(-2, "mg_conv_wgrad: channels must be multiples of 32");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout; p.Cin = Cin; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+    p.TW = np2(OW) < 8 ? np2(OW) : 8;
+    int th = kPixTile / p.TW;
+    p.TH = np2(OH) < th ? np2(OH) : th;
+    p.TN = kPixTile / (p.TW * p.TH);
+    p.tiles_w = (OW + p.TW - 1) / p.TW; p.tiles_h = (OH + p.TH - 1) / p.TH; p.tiles_n = (N + p.TN - 1) / p.TN;
+    p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    int BN = Cin >= 128 ? 128 : Cin;
+    if (Cin % BN != 0) BN = 32;
+    p.BN = BN;
+    p.m_tiles = (Cout + 127) / 128;
+    p.n_tiles = Cin / BN;
+    const int units = KH * KW * p.m_tiles * p.n_tiles;
+    int splits = (2 * num_sms() + units - 1) / units;
+    if (splits > p.pix_tiles) splits = p.pix_tiles;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    const int stage_bytes = 4 * kBoxBytes + (BN / 32) * kBoxBytes;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > kWgStagesMax) stages = kWgStagesMax;
+    p.stages = stages;
+    // TF32 x TF32 -> F32, A and B both MN-major (bits 15, 16), M = 128, N = BN
+    p.idesc = umma_idesc_tf32(128, BN) | (1u << 15) | (1u << 16);
+    int tc = np2(BN); p.tmem_cols = tc < 32 ? 32 : tc;
+    p.dw = dw;
+
+    CUtensorMap tmDY, tmX;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        int rc = encode_tensor_map(&tmDY, (void*)dy, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
+        cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        int rc = encode_tensor_map(&tmX, (void*)x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    if (splits > 1) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)Cout * KH * KW * Cin * sizeof(float), stream);
+        if (e != cudaSuccess) return set_error((int)e, "wgrad memset: %s", cudaGetErrorString(e));
+    }
+    static thread_local int attr_dev = -1;
+    int dev = 0; cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_error((int)e, "wgrad attr: %s", cudaGetErrorString(e));
+        attr_dev = dev;
+    }
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    wgrad_tf32_kernel<<<units * splits, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, p);
+    return check_launch("mg_conv_wgrad");
+}

@@ -70,7 +70,7 @@ def pack_weight_thin(w_oihw, cin_pad):
 
 # ------------------------------------------------------------------------------------------ convs
 def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_out=False, bias=None, res=None,
-               res_shift=0, pscale=None, pmul=None, blend=None, spade=None, bn=0, max_ctas=0):
+               res_shift=0, pscale=None, pmul=None, blend=None, spade=None, bn=0, max_ctas=0, out=None, out_hw=None, _extra=None):
     """Implicit-GEMM conv on tcgen05.  x: [N,H,W,Cin]; returns [N,OH,OW,cout].
 
     blend = (bf[N,OH,OW,cout], hair[N,MH,MW], back[N,MH,MW], mask_stride)
@@ -78,9 +78,13 @@ def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_o
     """
     _chk(x, "x"); _chk(wpack, "wpack"); _chk(bias, "bias"); _chk(res, "res"); _chk(pscale, "pscale"); _chk(pmul, "pmul")
     N, H, W, Cin = x.shape
-    OH = (H + 2 * pad - kh) // stride + 1
-    OW = (W + 2 * pad - kw) // stride + 1
-    out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32)
+    if out_hw is not None:
+        OH, OW = out_hw
+    else:
+        OH = (H + 2 * pad - kh) // stride + 1
+        OW = (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32)
     a = IgemmArgs()
     a.inp, a.wpack, a.out = _p(x), _p(wpack), _p(out)
     a.N, a.H, a.W, a.Cin = N, H, W, Cin
@@ -113,6 +117,9 @@ def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_o
         assert wpack.shape[0] == cout, (wpack.shape, cout)
     assert wpack.shape[1] == kh * kw * Cin, (wpack.shape, kh, kw, Cin)
     a.max_ctas = max_ctas
+    if _extra is not None:
+        for k_, v_ in _extra.items():
+            setattr(a, k_, v_)
     check(_lib.load().mg_conv_igemm(C.byref(a), _stream()), "mg_conv_igemm")
     return out
 
@@ -308,4 +315,65 @@ def avgpool3s2(x):
     OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
     out = torch.empty((N, OH, OW, Cc), device=x.device, dtype=torch.float32)
     check(_lib.load().mg_avgpool3s2(_p(x), _p(out), N, H, W, Cc, OH, OW, _stream()), "mg_avgpool3s2")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ backward
+def conv_wgrad(dy, x, kh, kw, stride=1, pad=0):
+    """Packed weight gradient [Cout][kh*kw*Cin] of an implicit-GEMM conv (tcgen05, split-K)."""
+    _chk(dy, "dy"); _chk(x, "x")
+    N, H, W, Cin = x.shape
+    _, OH, OW, Cout = dy.shape
+    dw = torch.empty((Cout, kh * kw * Cin), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_conv_wgrad(_p(dy), _p(x), _p(dw), N, H, W, Cin, OH, OW, Cout, kh, kw, stride, pad, _stream()),
+          "mg_conv_wgrad")
+    return dw
+
+
+def dgrad_geometry(k, stride, pad, r):
+    """Sub-kernel of the transposed conv for output parity r: (k0, J, pad') (see mg_pack_weight_dgrad)."""
+    k0 = (r + pad) % stride
+    J = (k - k0 + stride - 1) // stride
+    d0 = (r + pad - k0) // stride
+    return k0, J, J - 1 - d0
+
+
+def conv_dgrad(dy, w_oihw, in_hw, stride=1, pad=0, inv_sigma=None, out=None, accumulate=False):
+    """dX [N,H,W,Cin] of y = conv(x, w, stride, pad) given dY [N,OH,OW,Cout]; tcgen05 implicit GEMM on dY
+    with flipped/transposed (sub-)kernels, one launch per output parity class (stride^2)."""
+    _chk(dy, "dy"); _chk(w_oihw, "w")
+    N, OH, OW, Cout = dy.shape
+    O, I, KH, KW = w_oihw.shape
+    H, W = in_hw
+    if out is None:
+        out = torch.empty((N, H, W, I), device=dy.device, dtype=torch.float32)
+        if stride > 1 and (H < stride or W < stride):
+            out.zero_()
+    lib = _lib.load()
+    for rh in range(stride):
+        k0h, Jh, ph = dgrad_geometry(KH, stride, pad, rh)
+        for rw in range(stride):
+            k0w, Jw, pw = dgrad_geometry(KW, stride, pad, rw)
+            ah, aw = (H - rh + stride - 1) // stride, (W - rw + stride - 1) // stride
+            if ah <= 0 or aw <= 0:
+                continue
+            if Jh <= 0 or Jw <= 0:
+                if not accumulate:
+                    out[:, rh::stride, rw::stride].zero_()
+                continue
+            wp = torch.empty((I, Jh * Jw * O), device=dy.device, dtype=torch.float32)
+            check(lib.mg_pack_weight_dgrad(_p(w_oihw), _p(wp), O, I, KH, KW, stride, k0h, Jh, k0w, Jw, _p(inv_sigma), _stream()),
+                  "mg_pack_weight_dgrad")
+            extra = dict(pad_h_extra=ph, pad_w_extra=pw, out_stride=stride, out_off_h=rh, out_off_w=rw, OHF=H, OWF=W,
+                         accumulate=int(accumulate))
+            conv_igemm(dy, wp, I, Jh, Jw, 1, 0, out=out, out_hw=(ah, aw), _extra=extra)
+    return out
+
+
+def unpack_wgrad(dw_packed, shape_oihw, out=None, accumulate=False):
+    O, I, KH, KW = shape_oihw
+    if out is None:
+        out = torch.empty(shape_oihw, device=dw_packed.device, dtype=torch.float32)
+        accumulate = False
+    check(_lib.load().mg_unpack_wgrad(_p(dw_packed), _p(out), O, I, KH, KW, int(accumulate), _stream()), "mg_unpack_wgrad")
     return out

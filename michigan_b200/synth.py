@@ -19,7 +19,9 @@ def _rs(seed, key):
 
 
 def fill_state_dict(sd, seed=0, power_iters=30):
-    """In-place deterministic fill.  Conv weights ~ N(0, 1/fan_in); biases ~ N(0, 0.1^2); spectral-norm
+    """In-place deterministic fill.  Conv weights ~ N(0, 1/(3 fan_in)) - the variance of PyTorch's default
+    Conv2d init (kaiming_uniform, a=sqrt(5)), the regime in which SURVEY.md quotes the 1e-3 output bound
+    (output std ~ 0.1) - biases ~ N(0, 0.02^2); spectral-norm
     u, v are the converged power-iteration vectors of the filled weight (so eval-mode W/sigma is
     well-scaled, unlike a never-trained random u, v: SURVEY.md §7 'random-init eval is degenerate');
     BN running stats: mean 0, var 1 (calibrate them with a train-mode forward if needed)."""
@@ -36,10 +38,10 @@ def fill_state_dict(sd, seed=0, power_iters=30):
         elif key.endswith("weight_u") or key.endswith("weight_v"):
             continue  # after the weights
         elif key.endswith("bias"):
-            t.copy_(torch.from_numpy((r.standard_normal(tuple(t.shape)) * 0.1).astype(np.float32)))
+            t.copy_(torch.from_numpy((r.standard_normal(tuple(t.shape)) * 0.02).astype(np.float32)))
         elif t.dim() >= 2:
             fan_in = int(np.prod(t.shape[1:]))
-            t.copy_(torch.from_numpy((r.standard_normal(tuple(t.shape)) / np.sqrt(fan_in)).astype(np.float32)))
+            t.copy_(torch.from_numpy((r.standard_normal(tuple(t.shape)) / np.sqrt(3.0 * fan_in)).astype(np.float32)))
         else:
             t.copy_(torch.from_numpy(r.standard_normal(tuple(t.shape)).astype(np.float32)))
     for key in list(sd.keys()):
