@@ -84,6 +84,16 @@ typedef struct mg_igemm_args {
      * of an [N,OHF,OWF,Cout] tensor (0 = dense [N,OH,OW,Cout]); accumulate != 0: out += result. */
     int32_t pad_h_extra, pad_w_extra;
     int32_t out_stride, out_off_h, out_off_w, OHF, OWF, accumulate;
+    /* operand format: a_fmt 0 = fp32 storage read as TF32; 1 = fp16, 2 = bf16 storage (in/in_lo/wpack are
+     * then 16-bit arrays, Cin % 64 == 0).  split != 0: three-pass split precision A_hi*W_hi + A_lo*W_hi +
+     * A_hi*W_lo with in = A_hi, in_lo = A_lo and wpack = [CoutG][tap][hi|lo][Cin] (mg_pack_weight16).
+     * out_hi / out_lo: optional 16-bit copies of the result (hi = cvt(y), lo = cvt(y - hi)), fmt out16_fmt;
+     * `out` may then be null. */
+    const void* in_lo;
+    int32_t a_fmt, split;
+    void* out_hi;
+    void* out_lo;
+    int32_t out16_fmt;
 } mg_igemm_args;
 int mg_conv_igemm(const mg_igemm_args* a, void* stream);
 
@@ -96,6 +106,12 @@ int mg_pack_weight(const float* w_oihw, float* wpack, int O, int I, int KH, int 
  * rows [t*BN, t*BN+BN/2) = gamma channels t*BN/2.., rows [t*BN+BN/2, (t+1)*BN) = beta channels. */
 int mg_pack_weight_gb(const float* wg_oihw, const float* wb_oihw, float* wpack, int C, int I, int KH,
                       int KW, int BN, void* stream);
+/* 16-bit operand variants (fmt 1 = fp16, 2 = bf16): out[o][tap][hi|lo][i]; lo present iff split != 0,
+ * lo = cvt(w*inv_sigma - float(hi)).  The 3-pass split recovers ~16 (bf16) / ~22 (fp16) mantissa bits. */
+int mg_pack_weight16(const float* w_oihw, void* out, int O, int I, int KH, int KW, const float* inv_sigma, int fmt,
+                     int split, void* stream);
+int mg_pack_weight_gb16(const float* wg_oihw, const float* wb_oihw, void* out, int C, int I, int KH, int KW, int BN,
+                        int fmt, void* stream);
 
 /* Thin direct convolutions on CUDA cores (exact fp32): layers whose Cin is 3/4/7.
  * mode 0: zero padding; mode 1: reflection padding (MaskGAN_networks.py:120-121);
@@ -111,6 +127,10 @@ typedef struct mg_thin_args {
     int32_t act, round_out;
     const float* pscale;
     const float* pmul;
+    /* optional 16-bit copies of the output (operands of the next tensor-core conv); out may be null */
+    void* out_hi;
+    void* out_lo;
+    int32_t out16_fmt;
 } mg_thin_args;
 int mg_conv_thin(const mg_thin_args* a, void* stream);
 int mg_pack_weight_thin(const float* w_oihw, float* wt, int O, int I, int CinP, int KH, int KW, void* stream);
@@ -141,7 +161,7 @@ int mg_bn_from_running(const float* running_mean, const float* running_var, int 
 int mg_in_stats(const float* x, int N, long long HW, int C, double* sums /* [N][2][C] */, void* stream);
 /* ss: [N][2][C] float workspace that receives (rstd, -mean*rstd) */
 int mg_in_apply(const float* x, const double* sums, float* ss, float* y, int N, long long HW, int C, float eps, int act,
-                int round_out, const float* pmul, void* stream);
+                int round_out, const float* pmul, void* y_hi, void* y_lo, int out16_fmt, void* stream);
 
 /* Input preparation (generator.py:129-142; pix2pix_model.py:549-566).
  * seg4 [N,H,W,4] = (tag0, tag1, sin(2th)*hair, cos(2th)*hair), th = orient/255*pi; orient_c==2 passes
@@ -171,7 +191,8 @@ int mg_masked_mean_bcast(const float* x, const float* mref, const float* mtag, f
 /* F.interpolate(bilinear, align_corners=False) on NHWC (encoder.py:222-223). */
 int mg_resize_bilinear(const float* in, float* out, int N, int H, int W, int C, int OH, int OW, void* stream);
 /* nn.ReflectionPad2d(pad) on NHWC (MaskGAN_networks.py:120-121), optional TF32 (RNA) rounding. */
-int mg_reflect_pad(const float* in, float* out, int N, int H, int W, int C, int pad, int round_tf32, void* stream);
+int mg_reflect_pad(const float* in, float* out, int N, int H, int W, int C, int pad, int round_tf32, void* out_hi,
+                   void* out_lo, int out16_fmt, void* stream);
 
 /* Spectral norm for all SN convs of a network in three launches (torch SpectralNorm.compute_weight
  * as applied at architecture.py:38-42, normalization.py:28-29).  `descs` is a DEVICE array of

@@ -30,6 +30,8 @@ class IgemmArgs(C.Structure):
         ("pad_h_extra", C.c_int32), ("pad_w_extra", C.c_int32),
         ("out_stride", C.c_int32), ("out_off_h", C.c_int32), ("out_off_w", C.c_int32),
         ("OHF", C.c_int32), ("OWF", C.c_int32), ("accumulate", C.c_int32),
+        ("in_lo", c_f32p), ("a_fmt", C.c_int32), ("split", C.c_int32),
+        ("out_hi", c_f32p), ("out_lo", c_f32p), ("out16_fmt", C.c_int32),
     ]
 
 
@@ -42,6 +44,7 @@ class ThinArgs(C.Structure):
         ("pad_mode", C.c_int32), ("seg_resize", C.c_int32),
         ("act", C.c_int32), ("round_out", C.c_int32),
         ("pscale", c_f32p), ("pmul", c_f32p),
+        ("out_hi", c_f32p), ("out_lo", c_f32p), ("out16_fmt", C.c_int32),
     ]
 
 
@@ -55,6 +58,8 @@ SIGNATURES = {
     "mg_conv_igemm": [C.POINTER(IgemmArgs), _p],
     "mg_pack_weight": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
     "mg_pack_weight_gb": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_pack_weight16": [_p, _p, _i, _i, _i, _i, _p, _i, _i, _p],
+    "mg_pack_weight_gb16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_thin": [C.POINTER(ThinArgs), _p],
     "mg_pack_weight_thin": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_conv_img": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -63,7 +68,7 @@ SIGNATURES = {
     "mg_bn_finalize": [_p, _i, _d, _d, _f, _f, _i, _p, _p, _p, _p, _p, _p, _p],
     "mg_bn_from_running": [_p, _p, _i, _f, _p, _p, _p],
     "mg_in_stats": [_p, _i, _ll, _i, _p, _p],
-    "mg_in_apply": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _i, _p, _p],
+    "mg_in_apply": [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _i, _p, _p, _p, _i, _p],
     "mg_prep_seg": [_p, _p, _i, _p, _i, _i, _i, _p],
     "mg_prep_dinput": [_p, _p, _p, _i, _i, _i, _p],
     "mg_prep_bginput": [_p, _p, _p, _p, _i, _i, _i, _p],
@@ -71,7 +76,7 @@ SIGNATURES = {
     "mg_partial_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mg_masked_mean_bcast": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mg_resize_bilinear": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "mg_reflect_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_reflect_pad": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "mg_spectral_norm_batched": [_p, _i, _i, _i, _i, _f, _p],
     "mg_pack_weight_dgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "mg_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],

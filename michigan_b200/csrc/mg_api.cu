@@ -47,11 +47,11 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_tensor_map(CUtensorMap* map, void* gaddr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+int encode_tensor_map(CUtensorMap* map, void* gaddr, CUtensorMapDataType dtype, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                       const cuuint32_t* box, const cuuint32_t* estrides, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(-100, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, gaddr, dims, strides, box, estrides,
+    CUresult r = fn(map, dtype, (cuuint32_t)rank, gaddr, dims, strides, box, estrides,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cmath>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "mg_internal.h"
 
 namespace mg {
@@ -18,6 +20,18 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     if (act == MG_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
     if (act == MG_ACT_TANH) return tanhf(v);
     return v;
+}
+// 16-bit split: hi = cvt(v), lo = cvt(v - float(hi)); fmt 1 = fp16 (clamped to the finite range), 2 = bf16
+__device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+    if (fmt == 1) {
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
 }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -53,6 +67,47 @@ __global__ void pack_weight_gb_kernel(const float* __restrict__ wg, const float*
         const float* src = rr < half ? wg : wb;
         const int c = tile * half + (rr < half ? rr : rr - half);
         out[idx] = rtf32(src[(((long long)c * I + i) * KH + kh) * KW + kw]);
+    }
+}
+
+// 16-bit operands: out[o][tap][part][i], part = hi (and lo when split) of w*inv_sigma
+__global__ void pack_weight16_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int O, int I, int KH, int KW,
+                                     const float* __restrict__ inv_sigma, int fmt, int split) {
+    const long long total = (long long)O * KH * KW * I;
+    const float s = inv_sigma ? *inv_sigma : 1.f;
+    const int parts = split ? 2 : 1;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = idx % I;
+        long long t = idx / I;
+        const int kw = t % KW; t /= KW;
+        const int kh = t % KH;
+        const int o = t / KH;
+        const float v = w[(((long long)o * I + i) * KH + kh) * KW + kw] * s;
+        uint16_t hi, lo;
+        split16(v, fmt, hi, lo);
+        const size_t base = ((size_t)o * KH * KW + (size_t)(kh * KW + kw)) * parts * I;
+        out[base + i] = hi;
+        if (split) out[base + I + i] = lo;
+    }
+}
+__global__ void pack_weight_gb16_kernel(const float* __restrict__ wg, const float* __restrict__ wb, uint16_t* __restrict__ out,
+                                        int C, int I, int KH, int KW, int BN, int fmt) {
+    const long long total = 2LL * C * KH * KW * I;
+    const int half = BN / 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = idx % I;
+        long long t = idx / I;
+        const int kw = t % KW; t /= KW;
+        const int kh = t % KH;
+        const int R = t / KH;
+        const int tile = R / BN, rr = R % BN;
+        const float* src = rr < half ? wg : wb;
+        const int c = tile * half + (rr < half ? rr : rr - half);
+        uint16_t hi, lo;
+        split16(src[(((long long)c * I + i) * KH + kh) * KW + kw], fmt, hi, lo);
+        out[idx] = hi;
     }
 }
 
@@ -181,9 +236,25 @@ thin_conv_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) 
                         float v = act_fn(acc[p_][c] * ps + bv[c], a.act) * pm;
                         y[c] = a.round_out ? rtf32(v) : v;
                     }
-                    float* op = a.out + pix * Cout + c_base;
-                    if constexpr (CPL == 4) *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
-                    else *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]);
+                    if (a.out) {
+                        float* op = a.out + pix * Cout + c_base;
+                        if constexpr (CPL == 4) *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+                        else *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]);
+                    }
+                    if (a.out_hi) {
+                        uint16_t hi[CPL], lo[CPL];
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) split16(y[c], a.out16_fmt, hi[c], lo[c]);
+                        uint16_t* oh = reinterpret_cast<uint16_t*>(a.out_hi) + pix * Cout + c_base;
+                        uint16_t* ol = a.out_lo ? reinterpret_cast<uint16_t*>(a.out_lo) + pix * Cout + c_base : nullptr;
+                        if constexpr (CPL == 4) {
+                            *reinterpret_cast<uint2*>(oh) = make_uint2(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16));
+                            if (ol) *reinterpret_cast<uint2*>(ol) = make_uint2(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16));
+                        } else {
+                            *reinterpret_cast<uint32_t*>(oh) = hi[0] | ((uint32_t)hi[1] << 16);
+                            if (ol) *reinterpret_cast<uint32_t*>(ol) = lo[0] | ((uint32_t)lo[1] << 16);
+                        }
+                    }
                 }
             }
         }
@@ -392,7 +463,8 @@ __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __res
 }
 // InstanceNorm apply: x [N][HW][C], ss [N][2][C]
 __global__ void in_apply_kernel(const float* __restrict__ x, const float* __restrict__ ss, float* __restrict__ y,
-                                int N, long long HW, int C, int act, int round_, const float* __restrict__ pmul) {
+                                int N, long long HW, int C, int act, int round_, const float* __restrict__ pmul,
+                                uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int fmt16) {
     const int G = C / 4;
     const long long total = (long long)N * HW * G;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -411,7 +483,14 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const float* __rest
             float t = act_fn(r[i], act) * pm;
             r[i] = round_ ? rtf32(t) : t;
         }
-        reinterpret_cast<float4*>(y)[idx] = make_float4(r[0], r[1], r[2], r[3]);
+        if (y) reinterpret_cast<float4*>(y)[idx] = make_float4(r[0], r[1], r[2], r[3]);
+        if (y_hi) {
+            uint16_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split16(r[i], fmt16, hi[i], lo[i]);
+            reinterpret_cast<uint2*>(y_hi)[idx] = make_uint2(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16));
+            if (y_lo) reinterpret_cast<uint2*>(y_lo)[idx] = make_uint2(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16));
+        }
     }
 }
 
@@ -572,7 +651,7 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ in, float* __re
 
 // ReflectionPad2d(p) on NHWC, optional TF32 rounding (MaskGAN_networks.py:120-121,168)
 __global__ void reflect_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C, int p,
-                                   int round_) {
+                                   int round_, uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int fmt16) {
     const int G = C / 4;
     const int PH = H + 2 * p, PW = W + 2 * p;
     const long long total = (long long)N * PH * PW * G;
@@ -590,7 +669,15 @@ __global__ void reflect_pad_kernel(const float* __restrict__ in, float* __restri
         if (iw >= W) iw = 2 * W - 2 - iw;
         float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)n * H + ih) * W + iw) * C) + g);
         if (round_) { v.x = rtf32(v.x); v.y = rtf32(v.y); v.z = rtf32(v.z); v.w = rtf32(v.w); }
-        reinterpret_cast<float4*>(out)[idx] = v;
+        if (out) reinterpret_cast<float4*>(out)[idx] = v;
+        if (o_hi) {
+            const float r[4] = {v.x, v.y, v.z, v.w};
+            uint16_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split16(r[i], fmt16, hi[i], lo[i]);
+            reinterpret_cast<uint2*>(o_hi)[idx] = make_uint2(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16));
+            if (o_lo) reinterpret_cast<uint2*>(o_lo)[idx] = make_uint2(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16));
+        }
     }
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, long long HW,
@@ -692,7 +779,8 @@ extern "C" int mg_pack_weight_thin(const float* w, float* wt, int O, int I, int 
 }
 
 extern "C" int mg_conv_thin(const mg_thin_args* a, void* stream) {
-    if (!a || !a->in || !a->w || !a->out) return set_error(-1, "mg_conv_thin: null pointer");
+    if (!a || !a->in || !a->w || (!a->out && !a->out_hi)) return set_error(-1, "mg_conv_thin: null pointer");
+    if (a->out_hi && (a->out16_fmt < 1 || a->out16_fmt > 2)) return set_error(-6, "mg_conv_thin: out16_fmt must be 1 or 2");
     if (a->CinP != 4 && a->CinP != 8) return set_error(-2, "mg_conv_thin: CinP must be 4 or 8");
     if (a->Cout % 32 != 0 || a->Cout > 128) return set_error(-3, "mg_conv_thin: Cout %d unsupported (multiple of 32, <=128)", a->Cout);
     if (a->seg_resize > 0 && a->CinP != 4) return set_error(-4, "mg_conv_thin: seg_resize needs CinP 4");
@@ -782,12 +870,14 @@ extern "C" int mg_bn_from_running(const float* rm, const float* rv, int C, float
     return check_launch("mg_bn_from_running");
 }
 extern "C" int mg_in_apply(const float* x, const double* sums, float* ss, float* y, int N, long long HW, int C, float eps,
-                           int act, int round_out, const float* pmul, void* stream) {
-    if (!x || !sums || !y || !ss) return set_error(-1, "mg_in_apply: null pointer");
+                           int act, int round_out, const float* pmul, void* y_hi, void* y_lo, int out16_fmt, void* stream) {
+    if (!x || !sums || (!y && !y_hi) || !ss) return set_error(-1, "mg_in_apply: null pointer");
+    if (y_hi && (out16_fmt < 1 || out16_fmt > 2)) return set_error(-3, "mg_in_apply: out16_fmt must be 1 or 2");
     if (C % 4 != 0) return set_error(-2, "mg_in_apply: C%%4");
     in_finalize_kernel<<<cdiv((long long)N * C, 128), 128, 0, ST(stream)>>>(sums, ss, N, C, (double)HW, eps);
     count_launch();
-    in_apply_kernel<<<ew_grid((long long)N * HW * (C / 4)), 256, 0, ST(stream)>>>(x, ss, y, N, HW, C, act, round_out, pmul);
+    in_apply_kernel<<<ew_grid((long long)N * HW * (C / 4)), 256, 0, ST(stream)>>>(x, ss, y, N, HW, C, act, round_out, pmul,
+                                                                                 (uint16_t*)y_hi, (uint16_t*)y_lo, out16_fmt);
     return check_launch("mg_in_apply");
 }
 
@@ -858,11 +948,11 @@ extern "C" int mg_resize_bilinear(const float* in, float* out, int N, int H, int
     return check_launch("mg_resize_bilinear");
 }
 extern "C" int mg_reflect_pad(const float* in, float* out, int N, int H, int W, int C, int pad, int round_tf32,
-                              void* stream) {
-    if (!in || !out) return set_error(-1, "mg_reflect_pad: null pointer");
+                              void* out_hi, void* out_lo, int out16_fmt, void* stream) {
+    if (!in || (!out && !out_hi)) return set_error(-1, "mg_reflect_pad: null pointer");
     if (C % 4 != 0 || pad >= H || pad >= W) return set_error(-2, "mg_reflect_pad: C%%4==0 and pad < size required");
     reflect_pad_kernel<<<ew_grid((long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / 4)), 256, 0, ST(stream)>>>(
-        in, out, N, H, W, C, pad, round_tf32);
+        in, out, N, H, W, C, pad, round_tf32, (uint16_t*)out_hi, (uint16_t*)out_lo, out16_fmt);
     return check_launch("mg_reflect_pad");
 }
 
@@ -1006,4 +1096,20 @@ extern "C" int mg_unpack_wgrad(const float* dwp, float* dw_oihw, int O, int I, i
     if (!dwp || !dw_oihw) return set_error(-1, "mg_unpack_wgrad: null pointer");
     unpack_wgrad_kernel<<<ew_grid((long long)O * I * KH * KW), 256, 0, ST(stream)>>>(dwp, dw_oihw, O, I, KH, KW, accumulate);
     return check_launch("mg_unpack_wgrad");
+}
+
+extern "C" int mg_pack_weight16(const float* w, void* out, int O, int I, int KH, int KW, const float* inv_sigma, int fmt,
+                                int split, void* stream) {
+    if (!w || !out) return set_error(-1, "mg_pack_weight16: null pointer");
+    if (fmt < 1 || fmt > 2) return set_error(-2, "mg_pack_weight16: fmt must be 1 (fp16) or 2 (bf16)");
+    pack_weight16_kernel<<<ew_grid((long long)O * I * KH * KW), 256, 0, ST(stream)>>>(w, (uint16_t*)out, O, I, KH, KW, inv_sigma,
+                                                                                     fmt, split);
+    return check_launch("mg_pack_weight16");
+}
+extern "C" int mg_pack_weight_gb16(const float* wg, const float* wb, void* out, int C, int I, int KH, int KW, int BN, int fmt,
+                                   void* stream) {
+    if (!wg || !wb || !out) return set_error(-1, "mg_pack_weight_gb16: null pointer");
+    if (BN % 64 != 0 || (2 * C) % BN != 0) return set_error(-2, "mg_pack_weight_gb16: bad BN %d for C %d", BN, C);
+    pack_weight_gb16_kernel<<<ew_grid(2LL * C * I * KH * KW), 256, 0, ST(stream)>>>(wg, wb, (uint16_t*)out, C, I, KH, KW, BN, fmt);
+    return check_launch("mg_pack_weight_gb16");
 }

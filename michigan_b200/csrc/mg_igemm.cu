@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "mg_ptx.cuh"
 #include "mg_internal.h"
 
@@ -37,7 +39,11 @@ struct IgemmParams {
     int BN, n_tiles, num_tiles, kchunks, stages;
     uint32_t idesc, tmem_cols;
     int epi, act, round_out;
-    float* out;
+    int a_fmt, parts, kelem;      // operand format: 0 tf32 (32 ch / 128 B row), 1 fp16, 2 bf16 (64 ch / row); parts 1 or 3
+    float* out;                   // fp32 output (may be null when only 16-bit copies are wanted)
+    void* out_hi;                 // optional 16-bit copy of the output (operand of the next tensor-core conv)
+    void* out_lo;                 // optional 16-bit residual: cvt(y - float(hi))
+    int out16_fmt;                // 1 fp16, 2 bf16
     const float* bias;
     const float* res;
     int res_shift, RH, RW;
@@ -62,9 +68,38 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// 16 consecutive channels -> 16-bit hi (and optional lo = cvt(y - hi)) copies, 32 B each.
+__device__ __forceinline__ void store16(const IgemmParams& p, const float (&y)[16], size_t elem_off) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float a = y[2 * i], b = y[2 * i + 1];
+        if (p.out16_fmt == 1) {
+            const __half ha = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
+            const __half hb = __float2half_rn(fminf(fmaxf(b, -65504.f), 65504.f));
+            hi[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+            const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+            lo[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+        } else {
+            const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+            hi[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+            const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+            lo[i] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+        }
+    }
+    uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_hi) + elem_off);
+    ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    if (p.out_lo) {
+        uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + elem_off);
+        pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const IgemmParams p) {
+igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align the operand ring (SWIZZLE_128B atoms are 1024 B).
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,6 +116,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -101,7 +137,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int ksteps = p.KH * p.KW * p.kchunks;
+    const int ksteps = p.KH * p.KW * p.parts * p.kchunks;
     const int m_tiles_per_img = p.tiles_w * p.tiles_h;
 
     if (warp == 0) {
@@ -119,15 +155,22 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int iw0 = tw * p.TW * p.stride - p.pad_w;
                 const int ih0 = th * p.TH * p.stride - p.pad_h;
                 const int n0 = tn * p.TN;
+                const int bparts = p.parts == 3 ? 2 : 1;   // weight operand holds (hi) or (hi, lo) per tap
                 for (int tap = 0; tap < p.KH * p.KW; ++tap) {
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&empty_bar[st], ph ^ 1);
-                        uint8_t* sa = smem + (size_t)st * stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[st], tx);
-                        tma_load_4d(sa, &tmA, &full_bar[st], kc * 32, iw0 + kw, ih0 + kh, n0);
-                        tma_load_2d(sa + kABytes, &tmB, &full_bar[st], tap * p.Cin + kc * 32, nt * p.BN);
-                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                    for (int part = 0; part < p.parts; ++part) {
+                        // split precision: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
+                        const CUtensorMap* ta = part == 1 ? &tmA2 : &tmA;
+                        const int bsel = part == 2 ? 1 : 0;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(&empty_bar[st], ph ^ 1);
+                            uint8_t* sa = smem + (size_t)st * stage_bytes;
+                            mbar_arrive_expect_tx(&full_bar[st], tx);
+                            tma_load_4d(sa, ta, &full_bar[st], kc * p.kelem, iw0 + kw, ih0 + kh, n0);
+                            tma_load_2d(sa + kABytes, &tmB, &full_bar[st], (tap * bparts + bsel) * p.Cin + kc * p.kelem,
+                                        nt * p.BN);
+                            if (++st == p.stages) { st = 0; ph ^= 1; }
+                        }
                     }
                 }
             }
@@ -152,8 +195,10 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in 16 B units
-                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                                  (ks | k) != 0 ? 1u : 0u);
+                        if (p.a_fmt == 0)
+                            umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ks | k) != 0 ? 1u : 0u);
+                        else
+                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ks | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[st]);  // frees the smem stage when these MMAs retire
                     if (++st == p.stages) { st = 0; ph ^= 1; }
@@ -246,17 +291,20 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             y[i] *= pm;
                             if (p.round_out) y[i] = round_tf32(y[i]);
                         }
-                        float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
-                        if (p.accumulate) {
+                        if (p.out) {
+                            float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
+                            if (p.accumulate) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 o = op[i];
-                                y[4 * i] += o.x; y[4 * i + 1] += o.y; y[4 * i + 2] += o.z; y[4 * i + 3] += o.w;
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 o = op[i];
+                                    y[4 * i] += o.x; y[4 * i + 1] += o.y; y[4 * i + 2] += o.z; y[4 * i + 3] += o.w;
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                            for (int i = 0; i < 4; ++i)
+                                op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        }
+                        if (p.out_hi) store16(p, y, pix * p.Cout + c0);
                     }
                 }
             } else {
@@ -291,10 +339,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             y[i] = apply_act(y[i], p.act);
                             if (p.round_out) y[i] = round_tf32(y[i]);
                         }
-                        float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
+                        if (p.out) {
+                            float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + c0);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                            for (int i = 0; i < 4; ++i)
+                                op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        }
+                        if (p.out_hi) store16(p, y, pix * p.Cout + c0);
                     }
                 }
             }
@@ -320,8 +371,14 @@ static int next_pow2(int v) {
 }
 
 int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
-    if (!a || !a->in || !a->wpack || !a->out) return set_error(-1, "mg_conv_igemm: null pointer");
-    if (a->Cin % 32 != 0) return set_error(-2, "mg_conv_igemm: Cin must be a multiple of 32 (got %d)", a->Cin);
+    if (!a || !a->in || !a->wpack || (!a->out && !a->out_hi)) return set_error(-1, "mg_conv_igemm: null pointer");
+    if (a->a_fmt < 0 || a->a_fmt > 2) return set_error(-9, "mg_conv_igemm: a_fmt must be 0 (tf32), 1 (fp16) or 2 (bf16)");
+    const int kelem = a->a_fmt == 0 ? 32 : 64;
+    if (a->Cin % kelem != 0)
+        return set_error(-2, "mg_conv_igemm: Cin must be a multiple of %d (got %d)", kelem, a->Cin);
+    if (a->split && (a->a_fmt == 0 || !a->in_lo)) return set_error(-10, "mg_conv_igemm: split precision needs 16-bit operands and in_lo");
+    if (a->out_hi && (a->out16_fmt < 1 || a->out16_fmt > 2)) return set_error(-11, "mg_conv_igemm: out16_fmt must be 1 or 2");
+    if (a->out_lo && !a->out_hi) return set_error(-12, "mg_conv_igemm: out_lo without out_hi");
     const int coutg = a->epi == MG_EPI_SPADE ? 2 * a->Cout : a->Cout;
     int BN = a->BN;
     if (BN == 0) {
@@ -354,12 +411,14 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.BN = BN;
     p.n_tiles = coutg / BN;
     p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-    p.kchunks = a->Cin / 32;
+    p.kchunks = a->Cin / kelem;
+    p.a_fmt = a->a_fmt; p.parts = a->split ? 3 : 1; p.kelem = kelem;
+    p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
     const int stage_bytes = kABytes + BN * 128;
     int stages = (220 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
-    p.idesc = umma_idesc_tf32(128, BN);
+    p.idesc = a->a_fmt == 0 ? umma_idesc_tf32(128, BN) : umma_idesc_16(128, BN, a->a_fmt);
     int tc = next_pow2(2 * BN);
     p.tmem_cols = tc < 32 ? 32 : tc;
     p.epi = a->epi; p.act = a->act; p.round_out = a->round_out;
@@ -372,23 +431,28 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.x = a->x; p.x_shift = a->x_shift; p.XH = a->OH >> a->x_shift; p.XW = a->OW >> a->x_shift;
     p.nscale = a->nscale; p.nshift = a->nshift; p.gbias1 = a->gbias1; p.bbias = a->bbias;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmA2, tmB;
+    const int esz = a->a_fmt == 0 ? 4 : 2;
+    const CUtensorMapDataType dt = a->a_fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : a->a_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
-        cuuint64_t strides[3] = {(cuuint64_t)a->Cin * 4, (cuuint64_t)a->W * a->Cin * 4,
-                                 (cuuint64_t)a->H * a->W * a->Cin * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * a->stride), (cuuint32_t)(p.TH * a->stride), (cuuint32_t)p.TN};
+        cuuint64_t strides[3] = {(cuuint64_t)a->Cin * esz, (cuuint64_t)a->W * a->Cin * esz,
+                                 (cuuint64_t)a->H * a->W * a->Cin * esz};
+        cuuint32_t box[4] = {(cuuint32_t)kelem, (cuuint32_t)(p.TW * a->stride), (cuuint32_t)(p.TH * a->stride), (cuuint32_t)p.TN};
         cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
-        int rc = encode_tensor_map(&tmA, (void*)a->in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = encode_tensor_map(&tmA, (void*)a->in, dt, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = encode_tensor_map(&tmA2, (void*)(a->split ? a->in_lo : a->in), dt, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     {
-        const cuuint64_t ktot = (cuuint64_t)a->KH * a->KW * a->Cin;
+        const cuuint64_t ktot = (cuuint64_t)a->KH * a->KW * a->Cin * (a->split ? 2 : 1);
         cuuint64_t dims[2] = {ktot, (cuuint64_t)coutg};
-        cuuint64_t strides[1] = {ktot * 4};
-        cuuint32_t box[2] = {32, (cuuint32_t)BN};
+        cuuint64_t strides[1] = {ktot * esz};
+        cuuint32_t box[2] = {(cuuint32_t)kelem, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
-        int rc = encode_tensor_map(&tmB, (void*)a->wpack, 2, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = encode_tensor_map(&tmB, (void*)a->wpack, dt, 2, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
 
@@ -404,7 +468,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    igemm_tf32_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    igemm_tf32_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, "igemm launch: %s", cudaGetErrorString(e));

@@ -11,7 +11,7 @@ int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
-int encode_tensor_map(CUtensorMap* map, void* gaddr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+int encode_tensor_map(CUtensorMap* map, void* gaddr, CUtensorMapDataType dtype, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                       const cuuint32_t* box, const cuuint32_t* estrides, CUtensorMapSwizzle swizzle);
 
 inline int check_launch(const char* what) {

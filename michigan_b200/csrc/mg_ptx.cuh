@@ -122,6 +122,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with 16-bit operands (fp16 or bf16 per the instruction descriptor), fp32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
@@ -185,6 +195,18 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N) {
     d |= 2u << 10;                     // b_format = TF32
     d |= (uint32_t)(N >> 3) << 17;     // n_dim
     d |= (uint32_t)(M >> 4) << 24;     // m_dim
+    return d;
+}
+
+// fmt: 1 = F16 x F16, 2 = BF16 x BF16 (-> F32), K-major operands
+__host__ __device__ inline uint32_t umma_idesc_16(int M, int N, int fmt) {
+    uint32_t d = 0;
+    const uint32_t f = fmt == 2 ? 1u : 0u;  // F16 = 0, BF16 = 1
+    d |= 1u << 4;
+    d |= f << 7;
+    d |= f << 10;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
     return d;
 }
 

@@ -196,7 +196,7 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
         cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, 1, 1, 1};
-        int rc = encode_tensor_map(&tmDY, (void*)dy, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = encode_tensor_map(&tmDY, (void*)dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     {
@@ -204,7 +204,7 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        int rc = encode_tensor_map(&tmX, (void*)x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = encode_tensor_map(&tmX, (void*)x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     if (splits > 1) {

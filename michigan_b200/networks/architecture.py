@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.utils.spectral_norm as spectral_norm
 
-from .. import ops
+from .. import ops, precision
 from .normalization import SPADE
 from .prep import PackCache
 
@@ -57,14 +57,20 @@ class SPADEResnetBlock(nn.Module):
         if hasattr(conv, "weight_orig"):
             w, isg = conv.weight_orig, inv_sigma_of[conv]
             # the scale depends on u, v as well: rebuilt whenever the spectral batch ran
-            return ops.pack_weight(w.detach(), isg, True)
-        return self._cache.get(name, [conv.weight], lambda: ops.pack_weight(conv.weight.detach(), None, True))
+            return precision.pack_conv(w.detach(), isg, precision.conv_fmt(w.shape[1]))
+        fmt = precision.conv_fmt(conv.weight.shape[1])
+        return self._cache.get((name, fmt), [conv.weight], lambda: precision.pack_conv(conv.weight.detach(), None, fmt))
 
     def _spade_pack(self, name):
         sp = getattr(self, name)
         c = self._cache
-        wgb = c.get(name + ".gb", [sp.mlp_gamma.weight, sp.mlp_beta.weight],
-                    lambda: ops.pack_weight_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach()))
+        gfmt = precision.gb_fmt()
+        if gfmt == ops.TF32:
+            wgb = c.get(name + ".gb", [sp.mlp_gamma.weight, sp.mlp_beta.weight],
+                        lambda: ops.pack_weight_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach()))
+        else:
+            wgb = c.get(name + ".gb16", [sp.mlp_gamma.weight, sp.mlp_beta.weight],
+                        lambda: ops.pack_weight_gb16(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach(), gfmt))
         wsh = c.get(name + ".sh", [sp.mlp_shared[0].weight],
                     lambda: ops.pack_weight_thin(sp.mlp_shared[0].weight.detach(), 4))
         g1 = c.get(name + ".g1", [sp.mlp_gamma.bias], lambda: (sp.mlp_gamma.bias.detach() + 1.0).contiguous())
@@ -88,26 +94,31 @@ class SPADEResnetBlock(nn.Module):
             if self.learned_shortcut:
                 nss, nhs = self.norm_s.param_free_norm.scale_shift(x)
 
+        gfmt = precision.gb_fmt()
+
         def spade_act(name, src, shift, nscale, nshift, act):
+            cfmt = precision.conv_fmt(src.shape[-1])
+            """-> tensor-core operand (fmt, hi, lo) holding act(SPADE(src)) for the consumer conv."""
             wsh, bsh, wgb, g1, bb = self._spade_pack(name)
-            actv = ops.conv_thin(seg4, wsh, bsh, 128, 3, 3, 1, 1, seg_resize=R, act=ops.ACT_RELU, round_out=True, out_hw=(h, w))
+            kw_a, get_a = precision.out_spec(gfmt, False)
+            actv = get_a(ops.conv_thin(seg4, wsh, bsh, 128, 3, 3, 1, 1, seg_resize=R, act=ops.ACT_RELU, out_hw=(h, w), **kw_a))
             c = src.shape[-1]
-            return ops.conv_igemm(actv, wgb, c, 3, 3, 1, 1, act=act, round_out=True,
-                                  spade=(src, shift, nscale, nshift, g1, bb))
+            kw_h, get_h = precision.out_spec(cfmt, cfmt == ops.BF16)
+            return get_h(precision.conv(actv, wgb, c, 3, 3, 1, 1, act=act, spade=(src, shift, nscale, nshift, g1, bb), **kw_h))
 
         if self.learned_shortcut:
             hs_ = spade_act("norm_s", x, x_shift, nss, nhs, ops.ACT_NONE)
-            x_s = ops.conv_igemm(hs_, self._conv_pack("conv_s", inv_sigma_of), self.fout, 1, 1, 1, 0)
+            x_s = precision.conv(hs_, self._conv_pack("conv_s", inv_sigma_of), self.fout, 1, 1, 1, 0)
             res, res_shift = x_s, 0
             del hs_
         else:
             res, res_shift = x, x_shift
         h0 = spade_act("norm_0", x, x_shift, ns0, nh0, ops.ACT_LRELU)
-        dx = ops.conv_igemm(h0, self._conv_pack("conv_0", inv_sigma_of), self.fmiddle, 3, 3, 1, 1, bias=self.conv_0.bias.detach())
+        dx = precision.conv(h0, self._conv_pack("conv_0", inv_sigma_of), self.fmiddle, 3, 3, 1, 1, bias=self.conv_0.bias.detach())
         del h0
         ns1, nh1 = self.norm_1.param_free_norm.scale_shift(dx)[:2]
         h1 = spade_act("norm_1", dx, 0, ns1, nh1, ops.ACT_LRELU)
-        out = ops.conv_igemm(h1, self._conv_pack("conv_1", inv_sigma_of), self.fout, 3, 3, 1, 1, bias=self.conv_1.bias.detach(),
+        out = precision.conv(h1, self._conv_pack("conv_1", inv_sigma_of), self.fout, 3, 3, 1, 1, bias=self.conv_1.bias.detach(),
                              res=res, res_shift=res_shift, blend=blend)
         return out
 

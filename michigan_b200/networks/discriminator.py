@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, precision
 from .base_network import BaseNetwork
 from .normalization import get_nonspade_norm_layer
 from .prep import PackCache, SpectralNormBatch
@@ -71,15 +71,31 @@ class NLayerDiscriminator(BaseNetwork):
         c = self._cache
         conv0 = self.model0[0]
         w0 = c.get("m0", [conv0.weight], lambda: ops.pack_weight_thin(conv0.weight.detach(), 8))
-        x = ops.conv_thin(x8, w0, conv0.bias.detach(), conv0.out_channels, 4, 4, 2, self.padw, act=ops.ACT_LRELU, round_out=True)
+        # one-pass fp16 (or TF32): the discriminator is not under the generator's image-error bound
+        def as_operand(r, fmt):
+            """(feature fp32, operand) from a producer's return value."""
+            if fmt == ops.TF32:
+                return r, (ops.TF32, r, None)
+            return r[0], (fmt, r[1], None)
+
+        def kw_for(fmt):
+            return dict(round_out=True) if fmt == ops.TF32 else dict(out16=(fmt, False))
+
+        fmt = precision.gb_fmt(conv0.out_channels)
+        kw_o = kw_for(fmt)
+        x, xo = as_operand(ops.conv_thin(x8, w0, conv0.bias.detach(), conv0.out_channels, 4, 4, 2, self.padw, act=ops.ACT_LRELU, **kw_o), fmt)
         outs = [x]
         for n, conv in zip(range(1, self.n_layers), self.mid_convs()):
             if hasattr(conv, "weight_orig"):
-                wp = ops.pack_weight(conv.weight_orig.detach(), inv_sigma_of[conv], True)
-            else:
+                wp = ops.pack_weight(conv.weight_orig.detach(), inv_sigma_of[conv], True) if fmt == ops.TF32 else \
+                    ops.pack_weight16(conv.weight_orig.detach(), inv_sigma_of[conv], fmt, split=False)
+            elif fmt == ops.TF32:
                 wp = c.get("m%d" % n, [conv.weight], lambda conv=conv: ops.pack_weight(conv.weight.detach(), None, True))
-            raw = ops.conv_igemm(x, wp, conv.out_channels, 4, 4, self._strides[n], self.padw)
-            x = ops.instance_norm_act(raw, ops.ACT_LRELU, 1e-5, round_out=True)
+            else:
+                wp = c.get(("m%d" % n, fmt), [conv.weight], lambda conv=conv: ops.pack_weight16(conv.weight.detach(), None, fmt, split=False))
+            raw = precision.conv(xo, wp, conv.out_channels, 4, 4, self._strides[n], self.padw)
+            fmt = precision.gb_fmt(conv.out_channels)
+            x, xo = as_operand(ops.instance_norm_act(raw, ops.ACT_LRELU, 1e-5, **kw_for(fmt)), fmt)
             outs.append(x)
         last = getattr(self, "model%d" % self.n_layers)[0]
         outs.append(ops.conv_to1(x, last.weight.detach(), last.bias.detach(), self.padw))

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, precision
 from .base_network import BaseNetwork
 from .prep import PackCache
 
@@ -65,12 +65,14 @@ class ImageEncoder3(BaseNetwork):
         w1 = c.get("l1", [self.layer1.weight], lambda: ops.pack_weight_thin(self.layer1.weight.detach(), 4))
         x = ops.conv_thin(x, w1, self.layer1.bias.detach(), self.layer1.out_channels, 3, 3, 2, 1, pscale=ratio, pmul=upd)
         for i in range(2, 6):
-            # lrelu(IN(x)) * mask, rounded to TF32: operand of the next partial conv (partialconv2d.py:69)
-            x = ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5, round_out=True, pmul=upd)
+            # lrelu(IN(x)) * mask as a tensor-core operand of the next partial conv (partialconv2d.py:69)
+            fmt = precision.conv_fmt(x.shape[-1])
+            kw_o, get_o = precision.out_spec(fmt, fmt == ops.BF16)
+            xo = get_o(ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5, pmul=upd, **kw_o))
             ratio, upd_next = ops.partial_mask(upd, 3, 2, 1)
             layer = getattr(self, "layer%d" % i)
-            wp = c.get("l%d" % i, [layer.weight], lambda layer=layer: ops.pack_weight(layer.weight.detach(), None, True))
-            x = ops.conv_igemm(x, wp, layer.out_channels, 3, 3, 2, 1, bias=layer.bias.detach(), pscale=ratio, pmul=upd_next)
+            wp = c.get(("l%d" % i, fmt), [layer.weight], lambda layer=layer: precision.pack_conv(layer.weight.detach(), None, fmt))
+            x = precision.conv(xo, wp, layer.out_channels, 3, 3, 2, 1, bias=layer.bias.detach(), pscale=ratio, pmul=upd_next)
             upd = upd_next
         x = ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5)
         out = ops.masked_mean_bcast(x, mref, mtag)
@@ -154,9 +156,14 @@ class BackgroundEncode2(BaseNetwork):
         x = x0
         for name in ("layer1", "layer2", "layer3"):
             blk = getattr(self, name)
-            wp = c.get(name, [blk.conv.weight], lambda blk=blk: ops.pack_weight(blk.conv.weight.detach(), None, True))
-            xp = ops.reflect_pad(x, 1, round_tf32=True)
-            x = ops.conv_igemm(xp, wp, blk.conv.out_channels, 4, 4, 2, 0, bias=blk.conv.bias.detach(), act=ops.ACT_RELU)
+            fmt = precision.conv_fmt(x.shape[-1])
+            wp = c.get((name, fmt), [blk.conv.weight], lambda blk=blk: precision.pack_conv(blk.conv.weight.detach(), None, fmt))
+            if fmt == ops.TF32:
+                xp = (ops.TF32, ops.reflect_pad(x, 1, round_tf32=True), None)
+            else:
+                _, hi, lo = ops.reflect_pad(x, 1, out16=(fmt, True), want_f32=False)
+                xp = (fmt, hi, lo)
+            x = precision.conv(xp, wp, blk.conv.out_channels, 4, 4, 2, 0, bias=blk.conv.bias.detach(), act=ops.ACT_RELU)
             feats.append(x)
         return feats[::-1], back
 

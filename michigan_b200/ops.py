@@ -13,6 +13,23 @@ from ._lib import IgemmArgs, ThinArgs, check
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 EPI_BIAS, EPI_SPADE = 0, 1
+# tensor-core operand formats
+TF32, F16, BF16 = 0, 1, 2
+_T16 = {F16: torch.float16, BF16: torch.bfloat16}
+
+
+def _dt(fmt):
+    return torch.float32 if fmt == TF32 else _T16[fmt]
+
+
+def _alloc16(shape, device, out16):
+    """out16 = None | (fmt, want_lo) -> (hi, lo) tensors (or None)."""
+    if out16 is None:
+        return None, None
+    fmt, want_lo = out16
+    hi = torch.empty(shape, device=device, dtype=_T16[fmt])
+    lo = torch.empty(shape, device=device, dtype=_T16[fmt]) if want_lo else None
+    return hi, lo
 
 
 def _p(t):
@@ -60,6 +77,25 @@ def pack_weight_gb(wg, wb):
     return out
 
 
+def pack_weight16(w_oihw, inv_sigma=None, fmt=BF16, split=True):
+    """16-bit operand [O][tap][hi|lo][I] (lo only when split) of w * inv_sigma."""
+    _chk(w_oihw, "w"); _chk(inv_sigma, "inv_sigma")
+    O, I, KH, KW = w_oihw.shape
+    out = torch.empty((O, KH * KW * (2 if split else 1) * I), device=w_oihw.device, dtype=_T16[fmt])
+    check(_lib.load().mg_pack_weight16(_p(w_oihw), _p(out), O, I, KH, KW, _p(inv_sigma), fmt, int(split), _stream()),
+          "mg_pack_weight16")
+    return out
+
+
+def pack_weight_gb16(wg, wb, fmt=F16):
+    _chk(wg, "wg"); _chk(wb, "wb")
+    Cc, I, KH, KW = wg.shape
+    out = torch.empty((2 * Cc, KH * KW * I), device=wg.device, dtype=_T16[fmt])
+    check(_lib.load().mg_pack_weight_gb16(_p(wg), _p(wb), _p(out), Cc, I, KH, KW, spade_bn(Cc), fmt, _stream()),
+          "mg_pack_weight_gb16")
+    return out
+
+
 def pack_weight_thin(w_oihw, cin_pad):
     _chk(w_oihw, "w")
     O, I, KH, KW = w_oihw.shape
@@ -70,23 +106,30 @@ def pack_weight_thin(w_oihw, cin_pad):
 
 # ------------------------------------------------------------------------------------------ convs
 def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_out=False, bias=None, res=None,
-               res_shift=0, pscale=None, pmul=None, blend=None, spade=None, bn=0, max_ctas=0, out=None, out_hw=None, _extra=None):
+               res_shift=0, pscale=None, pmul=None, blend=None, spade=None, bn=0, max_ctas=0, out=None, out_hw=None, _extra=None,
+               a_fmt=TF32, x_lo=None, out16=None, want_f32=True):
     """Implicit-GEMM conv on tcgen05.  x: [N,H,W,Cin]; returns [N,OH,OW,cout].
 
     blend = (bf[N,OH,OW,cout], hair[N,MH,MW], back[N,MH,MW], mask_stride)
     spade = (xsrc[N,OH>>s,OW>>s,cout], x_shift, nscale[c], nshift[c], gbias1[c], bbias[c])
+    a_fmt: operand format of x / wpack (TF32 = fp32 storage, F16, BF16); x_lo: low part -> 3-pass split
+    precision (wpack from pack_weight16(split=True)).  out16=(fmt, want_lo): also emit 16-bit copies of
+    the result; with want_f32=False only those.  Returns out32, or (out32|None, hi, lo|None) with out16.
     """
-    _chk(x, "x"); _chk(wpack, "wpack"); _chk(bias, "bias"); _chk(res, "res"); _chk(pscale, "pscale"); _chk(pmul, "pmul")
+    _chk(x, "x", _dt(a_fmt)); _chk(wpack, "wpack", _dt(a_fmt)); _chk(x_lo, "x_lo", _dt(a_fmt)); _chk(bias, "bias"); _chk(res, "res"); _chk(pscale, "pscale"); _chk(pmul, "pmul")
     N, H, W, Cin = x.shape
     if out_hw is not None:
         OH, OW = out_hw
     else:
         OH = (H + 2 * pad - kh) // stride + 1
         OW = (W + 2 * pad - kw) // stride + 1
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32)
+    hi, lo = _alloc16((N, OH, OW, cout), x.device, out16)
     a = IgemmArgs()
     a.inp, a.wpack, a.out = _p(x), _p(wpack), _p(out)
+    a.a_fmt, a.split, a.in_lo = a_fmt, int(x_lo is not None), _p(x_lo)
+    a.out_hi, a.out_lo, a.out16_fmt = _p(hi), _p(lo), (out16[0] if out16 else 0)
     a.N, a.H, a.W, a.Cin = N, H, W, Cin
     a.OH, a.OW, a.Cout = OH, OW, cout
     a.KH, a.KW, a.stride, a.pad = kh, kw, stride, pad
@@ -96,18 +139,18 @@ def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_o
     a.bias, a.res, a.res_shift = _p(bias), _p(res), res_shift
     a.pscale, a.pmul = _p(pscale), _p(pmul)
     if res is not None:
-        assert tuple(res.shape) == (N, OH >> res_shift, OW >> res_shift, cout), (res.shape, out.shape, res_shift)
+        assert tuple(res.shape) == (N, OH >> res_shift, OW >> res_shift, cout), (res.shape, (N, OH, OW, cout), res_shift)
     if blend is not None:
         bf, hair, back, ms = blend
         _chk(bf, "bf"); _chk(hair, "hair"); _chk(back, "back")
-        assert tuple(bf.shape) == (N, OH, OW, cout), (bf.shape, out.shape)
+        assert tuple(bf.shape) == (N, OH, OW, cout), (bf.shape, (N, OH, OW, cout))
         a.bf, a.hair, a.back = _p(bf), _p(hair), _p(back)
         a.mask_stride, a.MH, a.MW = ms, hair.shape[-2], hair.shape[-1]
     if spade is not None:
         xs, x_shift, nscale, nshift, gbias1, bbias = spade
         for t, nm in ((xs, "spade.x"), (nscale, "nscale"), (nshift, "nshift"), (gbias1, "gbias1"), (bbias, "bbias")):
             _chk(t, nm)
-        assert tuple(xs.shape) == (N, OH >> x_shift, OW >> x_shift, cout), (xs.shape, out.shape, x_shift)
+        assert tuple(xs.shape) == (N, OH >> x_shift, OW >> x_shift, cout), (xs.shape, (N, OH, OW, cout), x_shift)
         assert wpack.shape[0] == 2 * cout
         a.x, a.x_shift = _p(xs), x_shift
         a.nscale, a.nshift, a.gbias1, a.bbias = _p(nscale), _p(nshift), _p(gbias1), _p(bbias)
@@ -115,18 +158,21 @@ def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_o
             a.BN = spade_bn(cout)
     else:
         assert wpack.shape[0] == cout, (wpack.shape, cout)
-    assert wpack.shape[1] == kh * kw * Cin, (wpack.shape, kh, kw, Cin)
+    assert wpack.shape[1] == kh * kw * Cin * (2 if x_lo is not None else 1), (wpack.shape, kh, kw, Cin)
     a.max_ctas = max_ctas
     if _extra is not None:
         for k_, v_ in _extra.items():
             setattr(a, k_, v_)
     check(_lib.load().mg_conv_igemm(C.byref(a), _stream()), "mg_conv_igemm")
+    if out16 is not None:
+        return out, hi, lo
     return out
 
 
 def conv_thin(x, wt, bias, cout, kh, kw, stride=1, pad=0, *, pad_mode=0, seg_resize=0, act=ACT_NONE, round_out=False,
-              pscale=None, pmul=None, out_hw=None):
-    """Direct conv for 3/4/7-channel inputs (channels padded to 4 or 8).  x: [N,H,W,CinP]."""
+              pscale=None, pmul=None, out_hw=None, out16=None, want_f32=True):
+    """Direct conv for 3/4/7-channel inputs (channels padded to 4 or 8).  x: [N,H,W,CinP].
+    out16=(fmt, want_lo): also write 16-bit copies; returns (out32|None, hi, lo|None) then."""
     _chk(x, "x"); _chk(wt, "wt"); _chk(bias, "bias"); _chk(pscale, "pscale"); _chk(pmul, "pmul")
     N, Hp, Wp, CinP = x.shape
     if seg_resize:
@@ -135,9 +181,11 @@ def conv_thin(x, wt, bias, cout, kh, kw, stride=1, pad=0, *, pad_mode=0, seg_res
         H, W = Hp, Wp
     OH = (H + 2 * pad - kh) // stride + 1
     OW = (W + 2 * pad - kw) // stride + 1
-    out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32)
+    out = torch.empty((N, OH, OW, cout), device=x.device, dtype=torch.float32) if want_f32 else None
+    hi, lo = _alloc16((N, OH, OW, cout), x.device, out16)
     a = ThinArgs()
     a.inp, a.w, a.bias, a.out = _p(x), _p(wt), _p(bias), _p(out)
+    a.out_hi, a.out_lo, a.out16_fmt = _p(hi), _p(lo), (out16[0] if out16 else 0)
     a.N, a.H, a.W, a.CinP = N, H, W, CinP
     a.OH, a.OW, a.Cout = OH, OW, cout
     a.KH, a.KW, a.stride, a.pad = kh, kw, stride, pad
@@ -145,6 +193,8 @@ def conv_thin(x, wt, bias, cout, kh, kw, stride=1, pad=0, *, pad_mode=0, seg_res
     a.act, a.round_out = act, int(round_out)
     a.pscale, a.pmul = _p(pscale), _p(pmul)
     check(_lib.load().mg_conv_thin(C.byref(a), _stream()), "mg_conv_thin")
+    if out16 is not None:
+        return out, hi, lo
     return out
 
 
@@ -204,17 +254,20 @@ def bn_from_running(running_mean, running_var, eps=1e-5):
     return nscale, nshift
 
 
-def instance_norm_act(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None):
-    """InstanceNorm2d(affine=False) followed by an activation, NHWC."""
+def instance_norm_act(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None, out16=None, want_f32=True):
+    """InstanceNorm2d(affine=False) followed by an activation, NHWC.  out16 as in conv_igemm."""
     _chk(x, "x"); _chk(pmul, "pmul")
     N, H, W, Cc = x.shape
     sums = torch.zeros((N, 2, Cc), device=x.device, dtype=torch.float64)
     lib = _lib.load()
     check(lib.mg_in_stats(_p(x), N, H * W, Cc, _p(sums), _stream()), "mg_in_stats")
     ss = torch.empty((N, 2, Cc), device=x.device, dtype=torch.float32)
-    y = torch.empty_like(x)
-    check(lib.mg_in_apply(_p(x), _p(sums), _p(ss), _p(y), N, H * W, Cc, eps, act, int(round_out), _p(pmul), _stream()),
-          "mg_in_apply")
+    y = torch.empty_like(x) if want_f32 else None
+    hi, lo = _alloc16(tuple(x.shape), x.device, out16)
+    check(lib.mg_in_apply(_p(x), _p(sums), _p(ss), _p(y), N, H * W, Cc, eps, act, int(round_out), _p(pmul), _p(hi), _p(lo),
+                          (out16[0] if out16 else 0), _stream()), "mg_in_apply")
+    if out16 is not None:
+        return y, hi, lo
     return y
 
 
@@ -282,11 +335,16 @@ def resize_bilinear(x, oh, ow):
     return out
 
 
-def reflect_pad(x, pad, round_tf32=False):
+def reflect_pad(x, pad, round_tf32=False, out16=None, want_f32=True):
     _chk(x, "x")
     N, H, W, Cc = x.shape
-    out = torch.empty((N, H + 2 * pad, W + 2 * pad, Cc), device=x.device, dtype=torch.float32)
-    check(_lib.load().mg_reflect_pad(_p(x), _p(out), N, H, W, Cc, pad, int(round_tf32), _stream()), "mg_reflect_pad")
+    shape = (N, H + 2 * pad, W + 2 * pad, Cc)
+    out = torch.empty(shape, device=x.device, dtype=torch.float32) if want_f32 else None
+    hi, lo = _alloc16(shape, x.device, out16)
+    check(_lib.load().mg_reflect_pad(_p(x), _p(out), N, H, W, Cc, pad, int(round_tf32), _p(hi), _p(lo),
+                                     (out16[0] if out16 else 0), _stream()), "mg_reflect_pad")
+    if out16 is not None:
+        return out, hi, lo
     return out
 
 

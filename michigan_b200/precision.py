@@ -1,0 +1,59 @@
+"""Tensor-core operand policy.
+
+  "mixed16" (default)  SPADE gamma/beta GEMMs (66 % of the generator FLOPs): fp16 operands, one pass -
+                       same 11-bit significand as TF32 at twice the issue rate; their inputs (ReLU of
+                       a 3x3 conv of a [-1,1] segmap) and weights are far inside the fp16 range.
+                       conv_0 / conv_1 / conv_s, background- and reference-encoder convs: bf16 hi+lo
+                       split of both operands, three passes (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32
+                       accumulate) = ~16 significand bits with bf16's full exponent range.  These convs
+                       feed batch-norm statistics and dominate the output error in TF32.
+                       Discriminator convs: fp16, one pass.
+  "tf32"               every tensor-core conv reads fp32 storage as TF32, one pass.
+
+Set with MICHIGAN_B200_PRECISION or precision.set_mode().
+"""
+import os
+
+from . import ops
+
+_mode = os.environ.get("MICHIGAN_B200_PRECISION", "mixed16")
+
+
+def set_mode(mode):
+    global _mode
+    if mode not in ("mixed16", "tf32"):
+        raise ValueError("precision mode must be 'mixed16' or 'tf32'")
+    _mode = mode
+
+
+def mode():
+    return _mode
+
+
+def gb_fmt(cin=128):
+    """Operand format of the SPADE gamma/beta GEMM and of the discriminator convs.  16-bit operands need
+    Cin % 64 == 0 (one 128 B swizzle row = 64 channels); other layers (ngf/ndf = 32 test nets) use TF32."""
+    return ops.F16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
+
+
+def conv_fmt(cin):
+    """Operand format of the split-precision convs (BF16 -> three passes) or TF32 (one pass)."""
+    return ops.BF16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
+
+
+def out_spec(fmt, split):
+    """(kwargs for a producer kernel, extractor) so that its output is a tensor-core operand of `fmt`."""
+    if fmt == ops.TF32:
+        return dict(round_out=True), (lambda r: (ops.TF32, r, None))
+    return dict(out16=(fmt, split), want_f32=False), (lambda r: (fmt, r[1], r[2]))
+
+
+def pack_conv(w, inv_sigma, fmt):
+    if fmt == ops.TF32:
+        return ops.pack_weight(w, inv_sigma, True)
+    return ops.pack_weight16(w, inv_sigma, fmt, split=(fmt == ops.BF16))
+
+
+def conv(operand, wpack, cout, kh, kw, stride, pad, **kw_):
+    fmt, hi, lo = operand
+    return ops.conv_igemm(hi, wpack, cout, kh, kw, stride, pad, a_fmt=fmt, x_lo=lo, **kw_)

@@ -50,7 +50,7 @@ def test_struct_layouts_match_the_header():
             decl = decl.strip()
             if not decl:
                 continue
-            names = re.sub(r"^(const\s+)?(float\*|int32_t|float)\s*", "", decl)
+            names = re.sub(r"^(const\s+)?(float\*|void\*|int32_t|float)\s*", "", decl)
             fields += [n.strip().lstrip("*") for n in names.split(",")]
         got = [("in" if f[0] == "inp" else f[0]) for f in st._fields_]
         assert got == fields, (cname, got, fields)

@@ -231,6 +231,86 @@ def group_misc():
     report("nhwc_to_nchw", ops.nhwc_to_nchw(nhwc(x8)), x8, 0)
 
 
+def group_f16():
+    """16-bit operand paths: fp16 one pass (vs fp16-rounded inputs, exact) and bf16 three-pass split
+    (vs full fp32 inputs: ~16-bit precision)."""
+    g = torch.Generator(device="cpu").manual_seed(21)
+    for (N, h, Cin, Cout, k, s_, p_) in ((2, 32, 64, 64, 3, 1, 1), (2, 33, 128, 256, 4, 2, 2), (1, 64, 256, 128, 3, 1, 1), (3, 8, 64, 64, 1, 1, 0)):
+        x = torch.randn(N, Cin, h, h, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)
+        b = torch.randn(Cout, generator=g).to(dev)
+        # fp16 one pass
+        xh = nhwc(x).half()
+        wp = ops.pack_weight16(w, None, ops.F16, split=False)
+        ref = F.conv2d(x.half().float(), w.half().float(), b, stride=s_, padding=p_)
+        got = ops.conv_igemm(xh, wp, Cout, k, k, s_, p_, bias=b, a_fmt=ops.F16)
+        torch.cuda.synchronize()
+        report("fp16 1-pass N%d %d %d->%d k%d s%d" % (N, h, Cin, Cout, k, s_), nchw(got), ref, 2e-5)
+        # bf16 split, operands produced by the kernels themselves
+        xn = nhwc(x)
+        hi = xn.bfloat16()
+        lo = (xn - hi.float()).bfloat16()
+        wp3 = ops.pack_weight16(w, None, ops.BF16, split=True)
+        ref32 = F.conv2d(x, w, b, stride=s_, padding=p_)
+        got = ops.conv_igemm(hi, wp3, Cout, k, k, s_, p_, bias=b, a_fmt=ops.BF16, x_lo=lo)
+        torch.cuda.synchronize()
+        report("bf16 3-pass N%d %d %d->%d k%d s%d (vs fp32)" % (N, h, Cin, Cout, k, s_), nchw(got), ref32, 6e-5)
+    # 16-bit copies written by the epilogues / producers
+    x = torch.randn(2, 64, 32, 32, generator=g).to(dev)
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
+    o32, hi, lo = ops.conv_igemm(nhwc(tf32_trunc(x)), ops.pack_weight(tf32_trunc(w)), 64, 3, 3, 1, 1, out16=(ops.BF16, True))
+    torch.cuda.synchronize()
+    report("epilogue bf16 hi+lo reconstructs fp32", hi.float() + lo.float(), o32, 2e-5)
+    o32, hi, lo = ops.conv_igemm(nhwc(tf32_trunc(x)), ops.pack_weight(tf32_trunc(w)), 64, 3, 3, 1, 1, out16=(ops.F16, False))
+    report("epilogue fp16 hi", hi.float(), o32.half().float(), 0)
+    y32, yh, yl = ops.instance_norm_act(nhwc(x), out16=(ops.BF16, True))
+    report("instance_norm bf16 hi+lo", yh.float() + yl.float(), y32, 2e-5)
+    p32, ph, pl = ops.reflect_pad(nhwc(x), 1, out16=(ops.BF16, True))
+    report("reflect_pad bf16 hi+lo", ph.float() + pl.float(), p32, 2e-5)
+    seg = torch.randn(2, 4, 64, 64, generator=g).to(dev)
+    ws = (torch.randn(128, 4, 3, 3, generator=g) / 6).to(dev)
+    bs = torch.randn(128, generator=g).to(dev)
+    a32, ah, _ = ops.conv_thin(nhwc(seg), ops.pack_weight_thin(ws, 4), bs, 128, 3, 3, 1, 1, seg_resize=2, act=1, out_hw=(32, 32),
+                               out16=(ops.F16, False))
+    report("thin conv fp16 copy", ah.float(), a32.half().float(), 0)
+    # SPADE fused, fp16 gamma/beta GEMM
+    C = 128
+    actv = torch.randn(2, 128, 32, 32, generator=g).to(dev).relu()
+    wg = (torch.randn(C, 128, 3, 3, generator=g) / 34.0).to(dev)
+    wb = (torch.randn(C, 128, 3, 3, generator=g) / 34.0).to(dev)
+    xs = torch.randn(2, C, 32, 32, generator=g).to(dev)
+    v1 = torch.ones(C, device=dev); v0 = torch.zeros(C, device=dev)
+    a16 = nhwc(actv).half()
+    gamma = F.conv2d(a16.float().permute(0, 3, 1, 2), wg.half().float(), None, padding=1)
+    beta = F.conv2d(a16.float().permute(0, 3, 1, 2), wb.half().float(), None, padding=1)
+    ref = F.leaky_relu(xs * (1 + gamma) + beta, 0.2)
+    _, hi, lo = ops.conv_igemm(a16, ops.pack_weight_gb16(wg, wb), C, 3, 3, 1, 1, act=2, a_fmt=ops.F16,
+                               spade=(nhwc(xs), 0, v1, v0, v1, v0), out16=(ops.BF16, True), want_f32=False)
+    torch.cuda.synchronize()
+    report("SPADE fp16 GEMM -> bf16 hi+lo", nchw(hi.float() + lo.float()), ref, 3e-5)
+
+
+def group_bwd():
+    """tcgen05 weight gradient (MN-major operands, split-K) and data gradient (transposed conv)."""
+    g = torch.Generator(device="cpu").manual_seed(31)
+    for (N, h, Cin, Cout, k, s_, p_) in ((2, 32, 64, 64, 3, 1, 1), (2, 32, 128, 256, 3, 1, 1), (2, 33, 64, 128, 4, 2, 2),
+                                         (2, 65, 64, 128, 4, 1, 2), (2, 34, 64, 64, 4, 2, 0), (2, 32, 64, 128, 3, 2, 1),
+                                         (3, 8, 128, 64, 1, 1, 0), (4, 64, 128, 128, 3, 1, 1)):
+        x = tf32_trunc(torch.randn(N, Cin, h, h, generator=g).to(dev)).requires_grad_(True)
+        w = tf32_trunc((torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)).requires_grad_(True)
+        y = F.conv2d(x, w, None, stride=s_, padding=p_)
+        dy = tf32_trunc(torch.randn(y.shape, generator=g).to(dev))
+        y.backward(dy)
+        tag = "N%d %d %d->%d k%d s%d p%d" % (N, h, Cin, Cout, k, s_, p_)
+        dwp = ops.conv_wgrad(nhwc(dy), nhwc(x.detach()), k, k, s_, p_)
+        dw = ops.unpack_wgrad(dwp, tuple(w.shape))
+        torch.cuda.synchronize()
+        report("wgrad " + tag, dw, w.grad, 5e-5)
+        dx = ops.conv_dgrad(nhwc(dy), w.detach(), (h, h), s_, p_)
+        torch.cuda.synchronize()
+        report("dgrad " + tag, nchw(dx), x.grad, 5e-5)
+
+
 def group_perf():
     # first timing of the headline GEMM shapes (up_3 gamma/beta and conv_0 at 512x512, N=8)
     from michigan_b200 import _lib
