@@ -31,15 +31,17 @@ struct WgradParams {
     float* dw;  // [Cout][KH*KW*Cin]
 };
 
-// MN-major, 128B swizzle: 32 contiguous elements per row, 8 rows (K) per 1024 B atom;
-// LBO = byte distance between consecutive 32-element blocks along M/N, SBO = between 8-row K groups.
+// MN-major TF32 operands must use the "128B swizzle with 32B atoms" layout (UMMA layout type 1,
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 contiguous fp32 (128 B), 4 rows (K) per
+// 512 B swizzle atom.  LBO = byte distance between consecutive 32-element blocks along M/N,
+// SBO = distance between 4-row K groups (512 B for a dense box); one K=8 MMA spans two groups.
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -196,7 +198,7 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
         cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, 1, 1, 1};
-        int rc = encode_tensor_map(&tmDY, (void*)dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = encode_tensor_map(&tmDY, (void*)dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     }
     {
@@ -204,7 +206,7 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        int rc = encode_tensor_map(&tmX, (void*)x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = encode_tensor_map(&tmX, (void*)x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     }
     if (splits > 1) {
