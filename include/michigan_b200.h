@@ -94,6 +94,7 @@ typedef struct mg_igemm_args {
     void* out_hi;
     void* out_lo;
     int32_t out16_fmt;
+    float* aux_out; /* MG_EPI_SPADE: optional [N,OH,OW,Cout] fp32 copy of (1 + gamma), saved for mg_spade_bwd */
 } mg_igemm_args;
 int mg_conv_igemm(const mg_igemm_args* a, void* stream);
 
@@ -224,6 +225,50 @@ int mg_pack_weight_dgrad(const float* w_oihw, float* out, int O, int I, int KH, 
                          int k0w, int Jw, const float* inv_sigma, void* stream);
 /* packed [O][KH*KW*I] weight gradient -> OIHW (accumulate != 0: +=). */
 int mg_unpack_wgrad(const float* dw_packed, float* dw_oihw, int O, int I, int KH, int KW, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward pass (autograd of the modules listed above; identities in SURVEY.md Appendix B).
+ * ------------------------------------------------------------------------------------------- */
+/* SPADE elementwise backward.  dh, h (forward output, for act'), g1 = 1+gamma (saved by the forward):
+ * [N,H,W,C]; x: [N,H>>x_shift,W>>x_shift,C].  Writes dgb [N,H,W,2C] = (dgamma|dbeta) in the packed row
+ * order of the forward gamma|beta operand (TF32-rounded: operand of the two gradient GEMMs), dxhat
+ * [N,H,W,C], and adds sum(dxhat), sum(dxhat*xhat) to sums [2*C] doubles (normalization.py:116 + BN). */
+int mg_spade_bwd(const float* dh, const float* h, const float* g1, const float* x, int x_shift, int N, int H, int W, int C,
+                 const float* nscale, const float* nshift, int act, int BN, float* dgb, float* dxhat, double* sums, void* stream);
+/* dx[N,hs,ws,C] (+)= nscale * sum over the 2^x_shift x 2^x_shift children of (g - m1 - xhat*m2), m = sums/count
+ * (batch-norm backward through a folded nearest upsample); sums == null: plain child sum (upsample backward). */
+int mg_bn_bwd_apply(const float* g, const float* x, int x_shift, int N, int hs, int ws, int C, const float* nscale,
+                    const float* nshift, const double* sums, double count, float* dx, int accumulate, void* stream);
+/* background blend backward (generator.py:186): dy = dout*(1-back), dbf (+)= dout*(1-hair). */
+int mg_blend_bwd(const float* dout, const float* hair, const float* back, int N, int H, int W, int C, int mask_stride, int MH,
+                 int MW, float* dy, float* dbf, int accumulate_bf, void* stream);
+/* dz = dy * act'(y) * pm1[pix] * pm2[pix] (y = forward output; null pointers skip a factor). */
+int mg_act_bwd(const float* dy, const float* y, float* dz, long long P, int C, int act, const float* pm1, const float* pm2,
+               int round_tf32, void* stream);
+/* InstanceNorm(+act,+mask) backward; ss = (rstd, shift) from mg_in_apply, sums [N][2][C] double workspace. */
+int mg_in_bwd(const float* df, const float* x, const float* ss, double* sums, float* dx, int N, long long HW, int C, int act,
+              const float* pmul, int round_tf32, void* stream);
+/* thin conv gradients: dwt [KH*KW][CinP][Cout] (zeroed here); dimg_nchw [N,3,H,W] += data gradient of input
+ * channels [c_lo, c_lo+3) (the generated image inside the discriminator input). */
+int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N, int H, int W, int CinP, int OH, int OW, int Cout, int KH,
+                  int KW, int stride, int pad, int pad_mode, int seg_resize, void* stream);
+int mg_thin_dgrad3(const float* dz, const float* wt, float* dimg_nchw, int N, int H, int W, int CinP, int OH, int OW, int Cout,
+                   int KH, int KW, int stride, int pad, int c_lo, void* stream);
+/* conv_img backward: dx [N,H,W,Cin], dw [Cout,Cin,3,3] and db [Cout] are ACCUMULATED (zero them first). */
+int mg_conv_img_bwd(const float* dy_nchw, const float* y_nchw, const float* x, const float* w, float* dz4_ws, float* dx,
+                    float* dw, float* db, int N, int H, int W, int Cin, int Cout, int act_in, int act_out, void* stream);
+int mg_conv_to1_bwd(const float* dl, const float* x, const float* w, float* dx, float* dw, float* db, int N, int H, int W,
+                    int Cin, int KH, int KW, int pad, int accumulate_dx, void* stream);
+int mg_avgpool3s2_bwd(const float* dout, float* din_accum, int N, int H, int W, int C, int OH, int OW, void* stream);
+int mg_reflect_pad_bwd(const float* dpad, float* dx, int N, int H, int W, int C, int pad, int accumulate, void* stream);
+int mg_resize_bilinear_bwd(const float* dout, float* din_zeroed, int N, int H, int W, int C, int OH, int OW, void* stream);
+int mg_masked_mean_bcast_bwd(const float* dout, const float* mref, const float* mtag, float* dx, int N, int h, int w, int C,
+                             int MH, int MW, void* stream);
+/* dW_orig (+)= (dWt - <dWt, W/sigma> u v^T) / sigma  (u, v constants: torch spectral_norm autograd). */
+int mg_spectral_norm_bwd(const float* dwt, const float* w_orig, const float* u, const float* v, const float* inv_sigma,
+                         double* dot_ws, float* dw, int O, long long K, int accumulate, void* stream);
+int mg_pack_weight_dgrad_gb(const float* wg, const float* wb, float* out, int C, int I, int BN, void* stream);
+int mg_unpack_wgrad_gb(const float* dw_packed, float* dwg, float* dwb, int C, int I, int BN, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,7 @@ class IgemmArgs(C.Structure):
         ("OHF", C.c_int32), ("OWF", C.c_int32), ("accumulate", C.c_int32),
         ("in_lo", c_f32p), ("a_fmt", C.c_int32), ("split", C.c_int32),
         ("out_hi", c_f32p), ("out_lo", c_f32p), ("out16_fmt", C.c_int32),
+        ("aux_out", c_f32p),
     ]
 
 
@@ -81,6 +82,22 @@ SIGNATURES = {
     "mg_pack_weight_dgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "mg_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_conv_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_spade_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p],
+    "mg_bn_bwd_apply": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _d, _p, _i, _p],
+    "mg_blend_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
+    "mg_act_bwd": [_p, _p, _p, _ll, _i, _i, _p, _p, _i, _p],
+    "mg_in_bwd": [_p, _p, _p, _p, _p, _i, _ll, _i, _i, _p, _i, _p],
+    "mg_thin_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_thin_dgrad3": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_conv_img_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_conv_to1_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_avgpool3s2_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_reflect_pad_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_resize_bilinear_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_masked_mean_bcast_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_spectral_norm_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _p],
+    "mg_pack_weight_dgrad_gb": [_p, _p, _p, _i, _i, _i, _p],
+    "mg_unpack_wgrad_gb": [_p, _p, _p, _i, _i, _i, _i, _p],
     "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -59,6 +59,7 @@ struct IgemmParams {
     const float* nshift;
     const float* gbias1;
     const float* bbias;
+    float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -329,10 +330,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const float4 sh = __ldg(reinterpret_cast<const float4*>(p.nshift + c0 + i));
                             const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gbias1 + c0 + i));
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bbias + c0 + i));
-                            y[i] = fmaf(fmaf(xv.x, sc.x, sh.x), g1.x + __uint_as_float(g[i]), bb.x + __uint_as_float(b[i]));
-                            y[i + 1] = fmaf(fmaf(xv.y, sc.y, sh.y), g1.y + __uint_as_float(g[i + 1]), bb.y + __uint_as_float(b[i + 1]));
-                            y[i + 2] = fmaf(fmaf(xv.z, sc.z, sh.z), g1.z + __uint_as_float(g[i + 2]), bb.z + __uint_as_float(b[i + 2]));
-                            y[i + 3] = fmaf(fmaf(xv.w, sc.w, sh.w), g1.w + __uint_as_float(g[i + 3]), bb.w + __uint_as_float(b[i + 3]));
+                            const float4 gs = make_float4(g1.x + __uint_as_float(g[i]), g1.y + __uint_as_float(g[i + 1]),
+                                                          g1.z + __uint_as_float(g[i + 2]), g1.w + __uint_as_float(g[i + 3]));
+                            if (p.aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + c0 + i) = gs;  // 1+gamma, kept for backward
+                            y[i] = fmaf(fmaf(xv.x, sc.x, sh.x), gs.x, bb.x + __uint_as_float(b[i]));
+                            y[i + 1] = fmaf(fmaf(xv.y, sc.y, sh.y), gs.y, bb.y + __uint_as_float(b[i + 1]));
+                            y[i + 2] = fmaf(fmaf(xv.z, sc.z, sh.z), gs.z, bb.z + __uint_as_float(b[i + 2]));
+                            y[i + 3] = fmaf(fmaf(xv.w, sc.w, sh.w), gs.w, bb.w + __uint_as_float(b[i + 3]));
                         }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -429,7 +433,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.bf = a->bf; p.hair = a->hair; p.back = a->back;
     p.mask_stride = a->mask_stride; p.MH = a->MH; p.MW = a->MW;
     p.x = a->x; p.x_shift = a->x_shift; p.XH = a->OH >> a->x_shift; p.XW = a->OW >> a->x_shift;
-    p.nscale = a->nscale; p.nshift = a->nshift; p.gbias1 = a->gbias1; p.bbias = a->bbias;
+    p.nscale = a->nscale; p.nshift = a->nshift; p.gbias1 = a->gbias1; p.bbias = a->bbias; p.aux = a->aux_out;
 
     CUtensorMap tmA, tmA2, tmB;
     const int esz = a->a_fmt == 0 ? 4 : 2;

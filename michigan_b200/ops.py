@@ -107,7 +107,7 @@ def pack_weight_thin(w_oihw, cin_pad):
 # ------------------------------------------------------------------------------------------ convs
 def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_out=False, bias=None, res=None,
                res_shift=0, pscale=None, pmul=None, blend=None, spade=None, bn=0, max_ctas=0, out=None, out_hw=None, _extra=None,
-               a_fmt=TF32, x_lo=None, out16=None, want_f32=True):
+               a_fmt=TF32, x_lo=None, out16=None, want_f32=True, aux=None):
     """Implicit-GEMM conv on tcgen05.  x: [N,H,W,Cin]; returns [N,OH,OW,cout].
 
     blend = (bf[N,OH,OW,cout], hair[N,MH,MW], back[N,MH,MW], mask_stride)
@@ -130,6 +130,7 @@ def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_o
     a.inp, a.wpack, a.out = _p(x), _p(wpack), _p(out)
     a.a_fmt, a.split, a.in_lo = a_fmt, int(x_lo is not None), _p(x_lo)
     a.out_hi, a.out_lo, a.out16_fmt = _p(hi), _p(lo), (out16[0] if out16 else 0)
+    a.aux_out = _p(aux)
     a.N, a.H, a.W, a.Cin = N, H, W, Cin
     a.OH, a.OW, a.Cout = OH, OW, cout
     a.KH, a.KW, a.stride, a.pad = kh, kw, stride, pad
@@ -435,3 +436,197 @@ def unpack_wgrad(dw_packed, shape_oihw, out=None, accumulate=False):
         accumulate = False
     check(_lib.load().mg_unpack_wgrad(_p(dw_packed), _p(out), O, I, KH, KW, int(accumulate), _stream()), "mg_unpack_wgrad")
     return out
+
+
+def chan_sum(x):
+    """Per-channel sum over all pixels of an NHWC tensor (bias gradients) -> [C] fp32."""
+    return bn_sums(x)[: x.shape[-1]].float()
+
+
+def spade_bwd(dh, h, g1, x, x_shift, nscale, nshift, act):
+    """-> (dgb [N,H,W,2C] packed gamma|beta grads, dxhat [N,H,W,C], sums [2C] float64)."""
+    for t, nm in ((dh, "dh"), (h, "h"), (g1, "g1"), (x, "x")):
+        _chk(t, nm)
+    N, H, W, Cc = dh.shape
+    dgb = torch.empty((N, H, W, 2 * Cc), device=dh.device, dtype=torch.float32)
+    dxhat = torch.empty_like(dh)
+    sums = torch.zeros(2 * Cc, device=dh.device, dtype=torch.float64)
+    check(_lib.load().mg_spade_bwd(_p(dh), _p(h), _p(g1), _p(x), x_shift, N, H, W, Cc, _p(nscale), _p(nshift), act, spade_bn(Cc),
+                                   _p(dgb), _p(dxhat), _p(sums), _stream()), "mg_spade_bwd")
+    return dgb, dxhat, sums
+
+
+def bn_bwd_apply(g, x, x_shift, nscale, nshift, sums, count, dx=None):
+    """dx (+)= BN backward of g through a folded 2^x_shift upsample (sums=None: plain child sum)."""
+    _chk(g, "g"); _chk(x, "x"); _chk(dx, "dx")
+    N, H, W, Cc = g.shape
+    hs, ws = H >> x_shift, W >> x_shift
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty((N, hs, ws, Cc), device=g.device, dtype=torch.float32)
+    check(_lib.load().mg_bn_bwd_apply(_p(g), _p(x), x_shift, N, hs, ws, Cc, _p(nscale), _p(nshift), _p(sums), float(count), _p(dx),
+                                      int(acc), _stream()), "mg_bn_bwd_apply")
+    return dx
+
+
+def blend_bwd(dout, hair, back, mask_stride, dbf=None):
+    _chk(dout, "dout"); _chk(hair, "hair"); _chk(back, "back"); _chk(dbf, "dbf")
+    N, H, W, Cc = dout.shape
+    dy = torch.empty_like(dout)
+    acc = dbf is not None
+    if dbf is None:
+        dbf = torch.empty_like(dout)
+    check(_lib.load().mg_blend_bwd(_p(dout), _p(hair), _p(back), N, H, W, Cc, mask_stride, hair.shape[-2], hair.shape[-1], _p(dy),
+                                   _p(dbf), int(acc), _stream()), "mg_blend_bwd")
+    return dy, dbf
+
+
+def act_bwd(dy, y, act, pm1=None, pm2=None, round_tf32=False):
+    _chk(dy, "dy"); _chk(y, "y"); _chk(pm1, "pm1"); _chk(pm2, "pm2")
+    Cc = dy.shape[-1]
+    dz = torch.empty_like(dy)
+    check(_lib.load().mg_act_bwd(_p(dy), _p(y), _p(dz), dy.numel() // Cc, Cc, act, _p(pm1), _p(pm2), int(round_tf32), _stream()),
+          "mg_act_bwd")
+    return dz
+
+
+def instance_norm_act_fwd(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None):
+    """Training variant of instance_norm_act: also returns the (rstd, shift) table needed by in_bwd."""
+    _chk(x, "x"); _chk(pmul, "pmul")
+    N, H, W, Cc = x.shape
+    sums = torch.zeros((N, 2, Cc), device=x.device, dtype=torch.float64)
+    lib = _lib.load()
+    check(lib.mg_in_stats(_p(x), N, H * W, Cc, _p(sums), _stream()), "mg_in_stats")
+    ss = torch.empty((N, 2, Cc), device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    check(lib.mg_in_apply(_p(x), _p(sums), _p(ss), _p(y), N, H * W, Cc, eps, act, int(round_out), _p(pmul), None, None, 0, _stream()),
+          "mg_in_apply")
+    return y, ss
+
+
+def in_bwd(df, x, ss, act=ACT_LRELU, pmul=None, round_tf32=False):
+    _chk(df, "df"); _chk(x, "x"); _chk(ss, "ss"); _chk(pmul, "pmul")
+    N, H, W, Cc = x.shape
+    sums = torch.empty((N, 2, Cc), device=x.device, dtype=torch.float64)
+    dx = torch.empty_like(x)
+    check(_lib.load().mg_in_bwd(_p(df), _p(x), _p(ss), _p(sums), _p(dx), N, H * W, Cc, act, _p(pmul), int(round_tf32), _stream()),
+          "mg_in_bwd")
+    return dx
+
+
+def thin_wgrad(x, dz, kh, kw, stride, pad, pad_mode=0, seg_resize=0, in_hw=None):
+    """dwt [kh*kw][CinP][Cout] of a thin conv; x is the (possibly full-resolution seg) input."""
+    _chk(x, "x"); _chk(dz, "dz")
+    N, OH, OW, Cout = dz.shape
+    CinP = x.shape[-1]
+    H, W = in_hw if seg_resize else (x.shape[1], x.shape[2])
+    dwt = torch.empty((kh * kw, CinP, Cout), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_thin_wgrad(_p(x), _p(dz), _p(dwt), N, H, W, CinP, OH, OW, Cout, kh, kw, stride, pad, pad_mode, seg_resize,
+                                    _stream()), "mg_thin_wgrad")
+    return dwt
+
+
+def thin_dgrad3(dz, wt, dimg_nchw, kh, kw, stride, pad, c_lo):
+    _chk(dz, "dz"); _chk(wt, "wt"); _chk(dimg_nchw, "dimg")
+    N, OH, OW, Cout = dz.shape
+    _, _, H, W = dimg_nchw.shape
+    check(_lib.load().mg_thin_dgrad3(_p(dz), _p(wt), _p(dimg_nchw), N, H, W, wt.shape[1], OH, OW, Cout, kh, kw, stride, pad, c_lo,
+                                     _stream()), "mg_thin_dgrad3")
+    return dimg_nchw
+
+
+def conv_img_bwd(dy_nchw, y_nchw, x, w_oihw, act_in=ACT_LRELU, act_out=ACT_TANH):
+    """-> (dx [N,H,W,Cin], dw [Cout,Cin,3,3], db [Cout])."""
+    for t, nm in ((dy_nchw, "dy"), (y_nchw, "y"), (x, "x"), (w_oihw, "w")):
+        _chk(t, nm)
+    N, H, W, Cin = x.shape
+    cout = w_oihw.shape[0]
+    ws = torch.empty((N, H, W, 4), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    dw = torch.zeros_like(w_oihw)
+    db = torch.zeros(cout, device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_conv_img_bwd(_p(dy_nchw), _p(y_nchw), _p(x), _p(w_oihw), _p(ws), _p(dx), _p(dw), _p(db), N, H, W, Cin, cout,
+                                      act_in, act_out, _stream()), "mg_conv_img_bwd")
+    return dx, dw, db
+
+
+def conv_to1_bwd(dl, x, w_oihw, pad, dx=None, want_dx=True):
+    """-> (dx (+= when given), dw, db) of the Cin->1 logits conv."""
+    _chk(dl, "dl"); _chk(x, "x"); _chk(w_oihw, "w"); _chk(dx, "dx")
+    N, H, W, Cin = x.shape
+    _, _, KH, KW = w_oihw.shape
+    acc = dx is not None
+    if dx is None and want_dx:
+        dx = torch.empty_like(x)
+    dw = torch.zeros_like(w_oihw)
+    db = torch.zeros(1, device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_conv_to1_bwd(_p(dl), _p(x), _p(w_oihw), _p(dx), _p(dw), _p(db), N, H, W, Cin, KH, KW, pad, int(acc), _stream()),
+          "mg_conv_to1_bwd")
+    return dx, dw, db
+
+
+def avgpool3s2_bwd(dout, din_accum):
+    _chk(dout, "dout"); _chk(din_accum, "din")
+    N, H, W, Cc = din_accum.shape
+    check(_lib.load().mg_avgpool3s2_bwd(_p(dout), _p(din_accum), N, H, W, Cc, dout.shape[1], dout.shape[2], _stream()),
+          "mg_avgpool3s2_bwd")
+    return din_accum
+
+
+def reflect_pad_bwd(dpad, pad, dx=None):
+    _chk(dpad, "dpad"); _chk(dx, "dx")
+    N, PH, PW, Cc = dpad.shape
+    H, W = PH - 2 * pad, PW - 2 * pad
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty((N, H, W, Cc), device=dpad.device, dtype=torch.float32)
+    check(_lib.load().mg_reflect_pad_bwd(_p(dpad), _p(dx), N, H, W, Cc, pad, int(acc), _stream()), "mg_reflect_pad_bwd")
+    return dx
+
+
+def resize_bilinear_bwd(dout, in_hw):
+    _chk(dout, "dout")
+    N, OH, OW, Cc = dout.shape
+    din = torch.zeros((N, in_hw[0], in_hw[1], Cc), device=dout.device, dtype=torch.float32)
+    check(_lib.load().mg_resize_bilinear_bwd(_p(dout), _p(din), N, in_hw[0], in_hw[1], Cc, OH, OW, _stream()), "mg_resize_bilinear_bwd")
+    return din
+
+
+def masked_mean_bcast_bwd(dout, mref, mtag):
+    _chk(dout, "dout"); _chk(mref, "mref"); _chk(mtag, "mtag")
+    N, h, w, Cc = dout.shape
+    dx = torch.empty_like(dout)
+    check(_lib.load().mg_masked_mean_bcast_bwd(_p(dout), _p(mref), _p(mtag), _p(dx), N, h, w, Cc, mref.shape[-2], mref.shape[-1],
+                                               _stream()), "mg_masked_mean_bcast_bwd")
+    return dx
+
+
+def spectral_norm_bwd(dwt_oihw, w_orig, u, v, inv_sigma, out=None):
+    """Gradient w.r.t. weight_orig given the gradient w.r.t. W/sigma (u, v treated as constants)."""
+    for t, nm in ((dwt_oihw, "dwt"), (w_orig, "w_orig"), (u, "u"), (v, "v"), (inv_sigma, "inv_sigma")):
+        _chk(t, nm)
+    O = w_orig.shape[0]
+    K = w_orig[0].numel()
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(w_orig)
+    dot = torch.empty(1, device=w_orig.device, dtype=torch.float64)
+    check(_lib.load().mg_spectral_norm_bwd(_p(dwt_oihw), _p(w_orig), _p(u), _p(v), _p(inv_sigma), _p(dot), _p(out), O, K, int(acc),
+                                           _stream()), "mg_spectral_norm_bwd")
+    return out
+
+
+def pack_weight_dgrad_gb(wg, wb):
+    _chk(wg, "wg"); _chk(wb, "wb")
+    Cc, I, _, _ = wg.shape
+    out = torch.empty((I, 9 * 2 * Cc), device=wg.device, dtype=torch.float32)
+    check(_lib.load().mg_pack_weight_dgrad_gb(_p(wg), _p(wb), _p(out), Cc, I, spade_bn(Cc), _stream()), "mg_pack_weight_dgrad_gb")
+    return out
+
+
+def unpack_wgrad_gb(dw_packed, c, i):
+    _chk(dw_packed, "dw_packed")
+    dwg = torch.empty((c, i, 3, 3), device=dw_packed.device, dtype=torch.float32)
+    dwb = torch.empty_like(dwg)
+    check(_lib.load().mg_unpack_wgrad_gb(_p(dw_packed), _p(dwg), _p(dwb), c, i, spade_bn(c), 0, _stream()), "mg_unpack_wgrad_gb")
+    return dwg, dwb
