@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = os.path.join(HERE, "golden", "small_ngf32_128.npz")
+GOLDEN = os.path.join(HERE, "golden", "golden_ngf64_128.npz")
 
 
 def load_golden():
