@@ -174,8 +174,8 @@ def run_native(a):
     from michigan_b200.pix2pix_model import Pix2PixModel
     from michigan_b200.synth import fill_state_dict, synthetic_batch
 
-    if a.workload != "gen_fwd":
-        raise SystemExit("workload %s is not implemented yet in this round (see DESIGN.md)" % a.workload)
+    if a.workload == "train_step":
+        return run_train_step(a, rank, world, local)
     torch.manual_seed(0)
     opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world)
     model = Pix2PixModel(opt)
@@ -272,6 +272,79 @@ def run_native(a):
             ips, ms_cpu, cores = cpu_generator_forward_ips(3, 1, 1)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": "3 timed forwards of 1 image (batch 1, same net/size) after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+TRAIN_GFLOP_PER_IMG = 4775.8  # G step + D step, hinge GAN + GAN-feature losses
+
+
+def run_train_step(a, rank, world, local):
+    """BASELINE.json configs[2]: full G+D train iteration (run_generator_one_step + run_discriminator_one_step),
+    batch 8 per GPU, 512x512 synthetic; secondary metric (`--workload train_step`)."""
+    import torch.distributed as dist
+    from michigan_b200 import _lib
+    from michigan_b200.options import make_opt
+    from michigan_b200.synth import fill_state_dict, synthetic_batch
+    from michigan_b200.trainer import Pix2PixTrainer
+    torch.manual_seed(0)
+    opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world, niter=50, niter_decay=0)
+    trainer = Pix2PixTrainer(opt)
+    m = trainer.pix2pix_model_on_one_gpu
+    fill_state_dict(m.netG.state_dict(), 0)
+    fill_state_dict(m.netD.state_dict(), 1)
+    m.train()
+    data = synthetic_batch(a.batch, SIZE, 1234 + rank)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        trainer.run_generator_one_step(dict(host))
+        trainer.run_discriminator_one_step(dict(host))
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = ms_total.item()
+    if rank == 0:
+        ms_step = ms_total / a.steps
+        losses = {k: float(v.mean()) for k, v in trainer.get_latest_losses().items()}
+        h2d = sum(v.numel() * v.element_size() for k, v in host.items()
+                  if torch.is_tensor(v) and k in ("label_ref", "label_tag", "image_ref", "image_tag", "orient", "noise")) * 2
+        value = world * a.batch * a.steps / (ms_total * 1e-3)
+        line = {
+            "metric": "512x512 images/sec (train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": "full G+D train iteration (hinge GAN + GAN-feature losses, Adam TTUR), netG=spadeb ngf64, "
+                                   "netD=multiscale ndf64, batch %d/GPU, 512x512 synthetic" % a.batch,
+                       "global_batch": a.batch * world, "parallelism": "dp%d" % world,
+                       "l2": "no explicit flush: multi-GB activations per step", "algorithmic_gflop_per_image": TRAIN_GFLOP_PER_IMG},
+            "achieved_tflops_step": TRAIN_GFLOP_PER_IMG * a.batch / ms_step,
+            # the step already starts from host (pinned) tensors and returns host-visible loss scalars
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(losses)},
+            "gpu_launches": launches, "clocks": clocks, "losses": losses,
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

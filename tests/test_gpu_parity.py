@@ -158,3 +158,69 @@ def test_eval_batch_independence_at_benchmark_size():
         one = {k: v[i:i + 1].contiguous() for k, v in pre.items()}
         assert torch.equal(out[i:i + 1], _run_G(G, one)), "sample %d differs between batched and single run" % i
     assert torch.isfinite(out).all() and out.abs().max() <= 1.0
+
+
+def _rel_l2(got_summary, ref_summary):
+    a, b = got_summary[4:].astype(np.float64), ref_summary[4:].astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+def test_train_iteration_losses_and_grads_vs_golden():
+    """One generator step and one discriminator step through the hand-written backward (TF32 gradient
+    GEMMs) against the reference trainer's losses and gradients stored in the golden fixture.
+    Tolerances: losses 1e-2 relative; per-tensor gradient relative L2 error <= 5e-2 on the stored
+    strided samples (the hinge loss is piecewise linear, element-wise maxima are not meaningful)."""
+    from helpers import summary
+    from michigan_b200.options import make_opt
+    from michigan_b200.pix2pix_model import Pix2PixModel
+    from michigan_b200.synth import synthetic_batch
+    z, cfg = load_golden()
+    torch.manual_seed(0)
+    opt = make_opt(is_train=True, ngf=cfg["ngf"], ndf=cfg["ndf"], crop_size=cfg["size"], batchSize=cfg["batch"])
+    model = Pix2PixModel(opt)
+    model.netG.load_state_dict(reference_layout_state("G", cfg, cfg["seed_G"]))
+    model.netD.load_state_dict(reference_layout_state("D", cfg, cfg["seed_D"]))
+    model.train()
+    opt_G, opt_D = model.create_optimizers(opt)
+    data = synthetic_batch(cfg["batch"], cfg["size"], cfg["data_seed"])
+
+    random.seed(cfg["py_seed"])
+    opt_G.zero_grad()
+    g_losses, fake = model(dict(data), mode="generator")
+    sum(g_losses.values()).mean().backward()
+    torch.cuda.synchronize()
+    got = [float(g_losses["GAN"].mean()), float(g_losses["GAN_Feat"].mean())]
+    print("G losses", got, "reference", z["g_losses"].tolist())
+    for a, b in zip(got, z["g_losses"]):
+        assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (got, z["g_losses"])
+    named = dict(model.netG.named_parameters())
+    worst = 0.0
+    for k in z.files:
+        if k.startswith("g_grad/"):
+            p = named[k[len("g_grad/"):]]
+            assert p.grad is not None, k
+            rel = _rel_l2(summary(p.grad, stride=101), z[k])
+            print("   %-45s rel L2 %.3e" % (k, rel))
+            worst = max(worst, rel)
+    assert worst <= 5e-2, worst
+    assert named["backgroud_enc.layer4.conv.weight"].grad is None
+    opt_G.step()
+
+    random.seed(cfg["py_seed"] + 1)
+    opt_D.zero_grad()
+    d_losses = model(dict(data), mode="discriminator")
+    sum(d_losses.values()).mean().backward()
+    torch.cuda.synchronize()
+    got = [float(d_losses["D_Fake"].mean()), float(d_losses["D_real"].mean())]
+    print("D losses", got, "reference", z["d_losses"].tolist())
+    for a, b in zip(got, z["d_losses"]):
+        assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (got, z["d_losses"])
+    namedD = dict(model.netD.named_parameters())
+    worst = 0.0
+    for k in z.files:
+        if k.startswith("d_grad/"):
+            rel = _rel_l2(summary(namedD[k[len("d_grad/"):]].grad, stride=53), z[k])
+            print("   %-45s rel L2 %.3e" % (k, rel))
+            worst = max(worst, rel)
+    assert worst <= 5e-2, worst
+    opt_D.step()
