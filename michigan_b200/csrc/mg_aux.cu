@@ -836,7 +836,7 @@ extern "C" int mg_conv_to1(const float* x, const float* w, const float* bias, fl
 }
 
 static int launch_stats(const float* x, int B, long long P, int C, double* sums, cudaStream_t st) {
-    if (C % 4 != 0 || C > 1024) return set_error(-2, "chan_stats: C %d unsupported", C);
+    if (C % 4 != 0 || C > 4096 || (C > 1024 && C % 1024 != 0)) return set_error(-2, "chan_stats: C %d unsupported", C);
     const int G = C / 4;
     const int tpr = G < 256 ? G : 256;
     const int rows = 256 / tpr;

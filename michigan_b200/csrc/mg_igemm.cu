@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "mg_ptx.cuh"
@@ -60,6 +61,7 @@ struct IgemmParams {
     const float* gbias1;
     const float* bbias;
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
+    int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default); scratch offset in smem
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -208,8 +210,157 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (++acc == 2) { acc = 0; aph ^= 1; }
             }
         }
+    } else if (p.epi_impl == 1) {
+        // ===================== epilogue warps: transposed, coalesced =====================
+        // TMEM gives each lane one accumulator ROW (pixel).  The raw accumulators of a 16/32-channel chunk
+        // are dumped to a warp-private smem scratch and read back transposed, so that in the arithmetic and
+        // in every global access a group of 4/8 lanes covers one pixel's contiguous channels (full 64/128 B
+        // segments) instead of 32 lanes touching 32 different lines.
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        float* scr = reinterpret_cast<float*>(smem + p.epi_off) + ew * (32 * 36);
+        const bool spade = p.epi == 1;
+        const int span = spade ? (p.BN >> 2) : (p.BN >> 1);   // channels this warp owns per tile
+        const int cw = (span % 32 == 0 && !p.epi_cw16) ? 32 : 16;
+        const int rs = cw + 4;
+        const int lpp = cw >> 2, ppp = 32 / lpp, passes = lpp;
+        const int q = lane % lpp, psub = lane / lpp;
+        const int twl = 31 - __clz(p.TW), thl = 31 - __clz(p.TH);
+        const int ch_tile = p.BN >> 1;
+        int acc = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int m = tile / p.n_tiles;
+            const int tw = m % p.tiles_w;
+            const int th = (m / p.tiles_w) % p.tiles_h;
+            const int tn = m / m_tiles_per_img;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+            for (int cb = 0; cb < span; cb += cw) {
+                const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
+                float4 av[8], bv[8];
+#pragma unroll 1
+                for (int part = 0; part < (spade ? 2 : 1); ++part) {
+                    for (int s0 = 0; s0 < cw; s0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(t_row + col + part * ch_tile + s0, v);
+                        tmem_ld_wait();
+                        float4* d = reinterpret_cast<float4*>(scr + lane * rs + s0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            d[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                               __uint_as_float(v[4 * i + 3]));
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < passes) {
+                            const float4 t = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
+                            if (part == 0) av[j] = t; else bv[j] = t;
+                        }
+                    __syncwarp();
+                }
+                const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
+                if (cch >= p.Cout) continue;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = bias4, sh4 = bias4, g14 = bias4, bb4 = bias4;
+                if (spade) {
+                    sc4 = __ldg(reinterpret_cast<const float4*>(p.nscale + cch));
+                    sh4 = __ldg(reinterpret_cast<const float4*>(p.nshift + cch));
+                    g14 = __ldg(reinterpret_cast<const float4*>(p.gbias1 + cch));
+                    bb4 = __ldg(reinterpret_cast<const float4*>(p.bbias + cch));
+                } else if (p.bias) {
+                    bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + cch));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j >= passes) continue;
+                    const int r = quarter * 32 + j * ppp + psub;
+                    const int ow = tw * p.TW + (r & (p.TW - 1));
+                    const int oh = th * p.TH + ((r >> twl) & (p.TH - 1));
+                    const int n = tn * p.TN + (r >> (twl + thl));
+                    if (ow >= p.OW || oh >= p.OH || n >= p.N) continue;
+                    const size_t pix = ((size_t)n * p.OHF + (size_t)oh * p.os + p.ooh) * p.OWF + (size_t)ow * p.os + p.oow;
+                    float y[4];
+                    if (spade) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(
+                            p.x + (((size_t)n * p.XH + (oh >> p.x_shift)) * p.XW + (ow >> p.x_shift)) * p.Cout + cch));
+                        const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
+                        if (p.aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + cch) = gs;
+                        y[0] = fmaf(fmaf(xv.x, sc4.x, sh4.x), gs.x, bb4.x + bv[j].x);
+                        y[1] = fmaf(fmaf(xv.y, sc4.y, sh4.y), gs.y, bb4.y + bv[j].y);
+                        y[2] = fmaf(fmaf(xv.z, sc4.z, sh4.z), gs.z, bb4.z + bv[j].z);
+                        y[3] = fmaf(fmaf(xv.w, sc4.w, sh4.w), gs.w, bb4.w + bv[j].w);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], p.act);
+                    } else {
+                        const float ps = p.pscale ? __ldg(p.pscale + pix) : 1.f;
+                        y[0] = fmaf(av[j].x, ps, bias4.x); y[1] = fmaf(av[j].y, ps, bias4.y);
+                        y[2] = fmaf(av[j].z, ps, bias4.z); y[3] = fmaf(av[j].w, ps, bias4.w);
+                        if (p.res) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(
+                                p.res + (((size_t)n * p.RH + (oh >> p.res_shift)) * p.RW + (ow >> p.res_shift)) * p.Cout + cch));
+                            y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], p.act);
+                        if (p.bf) {
+                            const size_t mp = ((size_t)n * p.MH + (size_t)oh * p.mask_stride) * p.MW + (size_t)ow * p.mask_stride;
+                            const float om_hair = 1.f - __ldg(p.hair + mp), om_back = 1.f - __ldg(p.back + mp);
+                            const float4 bfv = __ldg(reinterpret_cast<const float4*>(p.bf + pix * p.Cout + cch));
+                            y[0] = bfv.x * om_hair + y[0] * om_back; y[1] = bfv.y * om_hair + y[1] * om_back;
+                            y[2] = bfv.z * om_hair + y[2] * om_back; y[3] = bfv.w * om_hair + y[3] * om_back;
+                        }
+                        if (p.pmul) {
+                            const float pm = __ldg(p.pmul + pix);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) y[i] *= pm;
+                        }
+                    }
+                    if (p.round_out) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[i] = round_tf32(y[i]);
+                    }
+                    if (p.out) {
+                        float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + cch);
+                        if (p.accumulate) {
+                            const float4 o = *op;
+                            y[0] += o.x; y[1] += o.y; y[2] += o.z; y[3] += o.w;
+                        }
+                        *op = make_float4(y[0], y[1], y[2], y[3]);
+                    }
+                    if (p.out_hi) {
+                        uint32_t hi[2], lo[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float a = y[2 * i], b = y[2 * i + 1];
+                            if (p.out16_fmt == 1) {
+                                const __half ha = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
+                                const __half hb = __float2half_rn(fminf(fmaxf(b, -65504.f), 65504.f));
+                                hi[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+                                lo[i] = (uint32_t)__half_as_ushort(__float2half_rn(a - __half2float(ha))) |
+                                        ((uint32_t)__half_as_ushort(__float2half_rn(b - __half2float(hb))) << 16);
+                            } else {
+                                const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+                                hi[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+                                lo[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a - __bfloat162float(ha))) |
+                                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b - __bfloat162float(hb))) << 16);
+                            }
+                        }
+                        const size_t eo = pix * p.Cout + cch;
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_hi) + eo) = make_uint2(hi[0], hi[1]);
+                        if (p.out_lo) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + eo) = make_uint2(lo[0], lo[1]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
     } else {
-        // ===================== epilogue warps =====================
+        // ===================== epilogue warps (row-per-lane reference implementation) =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;           // TMEM lane quarter this warp may access
         const int half = ew >> 2;               // column half handled by this warp
@@ -419,9 +570,14 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.a_fmt = a->a_fmt; p.parts = a->split ? 3 : 1; p.kelem = kelem;
     p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
     const int stage_bytes = kABytes + BN * 128;
-    int stages = (220 * 1024) / stage_bytes;
+    static const int epi_impl_env = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
+    static const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 0;
+    p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
+    const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * 36 * 4 : 0;
+    int stages = (227 * 1024 - 1024 - 512 - scratch_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
+    p.epi_off = stages * stage_bytes + 512;
     p.idesc = a->a_fmt == 0 ? umma_idesc_tf32(128, BN) : umma_idesc_16(128, BN, a->a_fmt);
     int tc = next_pow2(2 * BN);
     p.tmem_cols = tc < 32 ? 32 : tc;
@@ -460,7 +616,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         if (rc) return rc;
     }
 
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + scratch_bytes;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);

@@ -311,36 +311,64 @@ def group_bwd():
         report("dgrad " + tag, nchw(dx), x.grad, 5e-5)
 
 
+def _time(fn, iters=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def group_perf():
-    # first timing of the headline GEMM shapes (up_3 gamma/beta and conv_0 at 512x512, N=8)
-    from michigan_b200 import _lib
+    """Headline GEMM shapes (N=8) in the three operand modes."""
     for (N, h, Cin, C, spade) in ((8, 512, 128, 128, True), (8, 512, 128, 64, False), (8, 256, 128, 256, True),
-                                  (8, 128, 128, 512, True), (8, 64, 1024, 512, False)):
+                                  (8, 256, 256, 128, False), (8, 64, 1024, 512, False)):
         x = torch.randn(N, h, h, Cin, device=dev)
+        xs = torch.randn(N, h, h, C, device=dev)
+        v = torch.ones(C, device=dev)
+        w = torch.randn(C, Cin, 3, 3, device=dev) / 34
+        b = torch.zeros(C, device=dev)
         if spade:
-            wg = torch.randn(C, Cin, 3, 3, device=dev) / 34
-            wp = ops.pack_weight_gb(wg, wg)
-            xs = torch.randn(N, h, h, C, device=dev)
-            v = torch.ones(C, device=dev)
-            args = dict(act=2, spade=(xs, 0, v, v, v, v), round_out=True)
             flops = 2.0 * N * h * h * 9 * Cin * 2 * C
+            wp32, wp16 = ops.pack_weight_gb(w, w), ops.pack_weight_gb16(w, w)
+            x16 = x.half()
+            t_tf32 = _time(lambda: ops.conv_igemm(x, wp32, C, 3, 3, 1, 1, act=2, spade=(xs, 0, v, v, v, v), round_out=True))
+            t_f16 = _time(lambda: ops.conv_igemm(x16, wp16, C, 3, 3, 1, 1, act=2, spade=(xs, 0, v, v, v, v), a_fmt=ops.F16,
+                                                 out16=(ops.BF16, True), want_f32=False))
+            print("perf SPADE N%d %dx%d Cin%d C%d: tf32 %.3f ms %.0f TF/s | fp16->bf16 hi/lo %.3f ms %.0f TF/s" %
+                  (N, h, h, Cin, C, t_tf32, flops / t_tf32 / 1e9, t_f16, flops / t_f16 / 1e9), flush=True)
         else:
-            w = torch.randn(C, Cin, 3, 3, device=dev) / 34
-            wp = ops.pack_weight(w)
-            args = dict(bias=torch.zeros(C, device=dev))
             flops = 2.0 * N * h * h * 9 * Cin * C
-        for _ in range(2):
-            ops.conv_igemm(x, wp, C, 3, 3, 1, 1, **args)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            ops.conv_igemm(x, wp, C, 3, 3, 1, 1, **args)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        print("perf N%d %dx%d Cin%d C%d spade=%d: %.3f ms  %.1f TFLOP/s" % (N, h, h, Cin, C, spade, ms, flops / ms / 1e9),
-              flush=True)
+            wp32, wp3 = ops.pack_weight(w), ops.pack_weight16(w, None, ops.BF16, True)
+            hi = x.bfloat16(); lo = (x - hi.float()).bfloat16()
+            t_tf32 = _time(lambda: ops.conv_igemm(x, wp32, C, 3, 3, 1, 1, bias=b))
+            t_b3 = _time(lambda: ops.conv_igemm(hi, wp3, C, 3, 3, 1, 1, bias=b, a_fmt=ops.BF16, x_lo=lo))
+            print("perf conv  N%d %dx%d Cin%d C%d: tf32 %.3f ms %.0f TF/s | bf16x3 %.3f ms %.0f TF/s (useful)" %
+                  (N, h, h, Cin, C, t_tf32, flops / t_tf32 / 1e9, t_b3, flops / t_b3 / 1e9), flush=True)
+    # thin convs
+    seg = torch.randn(8, 512, 512, 4, device=dev)
+    ws = ops.pack_weight_thin(torch.randn(128, 4, 3, 3, device=dev), 4)
+    bs = torch.zeros(128, device=dev)
+    t = _time(lambda: ops.conv_thin(seg, ws, bs, 128, 3, 3, 1, 1, seg_resize=1, act=1, out_hw=(512, 512), out16=(ops.F16, False), want_f32=False))
+    print("perf mlp_shared 8x512x512 -> fp16: %.3f ms (%.2f TB/s written)" % (t, 8 * 512 * 512 * 128 * 2 / t / 1e9), flush=True)
+    img = torch.randn(8, 512, 512, 4, device=dev)
+    w7 = ops.pack_weight_thin(torch.randn(64, 3, 7, 7, device=dev), 4)
+    t = _time(lambda: ops.conv_thin(img, w7, torch.zeros(64, device=dev), 64, 7, 7, 1, 3, pad_mode=1, act=1))
+    print("perf bg conv1 k7 8x512x512: %.3f ms" % t, flush=True)
+    # backward GEMMs
+    dy = torch.randn(8, 256, 256, 128, device=dev)
+    xa = torch.randn(8, 256, 256, 256, device=dev)
+    wq = torch.randn(128, 256, 3, 3, device=dev) / 48
+    flops = 2.0 * 8 * 256 * 256 * 9 * 256 * 128
+    t = _time(lambda: ops.conv_wgrad(dy, xa, 3, 3, 1, 1))
+    print("perf wgrad 8x256x256 256->128: %.3f ms %.0f TF/s" % (t, flops / t / 1e9), flush=True)
+    t = _time(lambda: ops.conv_dgrad(dy, wq, (256, 256), 1, 1))
+    print("perf dgrad 8x256x256 256->128: %.3f ms %.0f TF/s" % (t, flops / t / 1e9), flush=True)
 
 
 if __name__ == "__main__":
