@@ -242,11 +242,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int cb = 0; cb < span; cb += cw) {
                 const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
                 float4 av[8], bv[8];
-#pragma unroll 1
-                for (int part = 0; part < (spade ? 2 : 1); ++part) {
+                // TMEM chunk -> scratch (row per lane) -> registers (transposed: lanes cover contiguous channels)
+                auto load_chunk = [&](int colbase, float4 (&dst)[8]) {
                     for (int s0 = 0; s0 < cw; s0 += 16) {
                         uint32_t v[16];
-                        tmem_ld16(t_row + col + part * ch_tile + s0, v);
+                        tmem_ld16(t_row + (uint32_t)(colbase + s0), v);
                         tmem_ld_wait();
                         float4* d = reinterpret_cast<float4*>(scr + lane * rs + s0);
 #pragma unroll
@@ -257,12 +257,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (j < passes) {
-                            const float4 t = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
-                            if (part == 0) av[j] = t; else bv[j] = t;
-                        }
+                        if (j < passes) dst[j] = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
                     __syncwarp();
-                }
+                };
+                load_chunk(col, av);
+                if (spade) load_chunk(col + ch_tile, bv);
                 const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
                 if (cch >= p.Cout) continue;
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = bias4, sh4 = bias4, g14 = bias4, bb4 = bias4;
@@ -570,7 +569,9 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.a_fmt = a->a_fmt; p.parts = a->split ? 3 : 1; p.kelem = kelem;
     p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
     const int stage_bytes = kABytes + BN * 128;
-    static const int epi_impl_env = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
+    static const int epi_impl_bias = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
+    static const int epi_impl_spade = getenv("MG_EPI_IMPL_SPADE") ? atoi(getenv("MG_EPI_IMPL_SPADE")) : epi_impl_bias;
+    const int epi_impl_env = a->epi == MG_EPI_SPADE ? epi_impl_spade : epi_impl_bias;
     static const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 0;
     p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
     const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * 36 * 4 : 0;

@@ -311,6 +311,164 @@ def group_bwd():
         report("dgrad " + tag, nchw(dx), x.grad, 5e-5)
 
 
+def group_bwd2():
+    """Backward CUDA-core kernels against torch autograd (fp32, GPU)."""
+    g = torch.Generator(device="cpu").manual_seed(41)
+    # ---- SPADE elementwise backward + BN backward (through a folded 2x upsample)
+    for (N, h, C, xs, act) in ((2, 16, 64, 0, 2), (2, 16, 128, 1, 2), (1, 8, 32, 1, 0)):
+        hs = h >> xs
+        x = torch.randn(N, C, hs, hs, generator=g).to(dev).requires_grad_(True)
+        gamma = (torch.randn(N, C, h, h, generator=g).to(dev) * 0.3).requires_grad_(True)
+        beta = (torch.randn(N, C, h, h, generator=g).to(dev) * 0.3).requires_grad_(True)
+        xu = F.interpolate(x, scale_factor=2 ** xs, mode="nearest") if xs else x
+        mean = xu.mean(dim=(0, 2, 3), keepdim=True)
+        var = xu.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+        rstd = 1 / torch.sqrt(var + 1e-5)
+        xhat = (xu - mean) * rstd
+        p_ = xhat * (1 + gamma) + beta
+        hh = F.leaky_relu(p_, 0.2) if act == 2 else p_
+        dh = torch.randn(N, C, h, h, generator=g).to(dev)
+        hh.backward(dh)
+        ns = rstd.view(-1).detach().contiguous()
+        nh = (-mean.view(-1) * rstd.view(-1)).detach().contiguous()
+        dgb, dxhat, sums = ops.spade_bwd(nhwc(dh), nhwc(hh.detach()), nhwc((1 + gamma).detach()), nhwc(x.detach()), xs, ns, nh, act)
+        dx = ops.bn_bwd_apply(dxhat, nhwc(x.detach()), xs, ns, nh, sums, N * h * h)
+        torch.cuda.synchronize()
+        bn = ops.spade_bn(C); half = bn // 2
+        ch = torch.arange(C, device=dev); gi = (ch // half) * bn + ch % half; bi = gi + half
+        report("spade_bwd dgamma C%d xs%d" % (C, xs), nchw(dgb[..., gi].contiguous()), gamma.grad, 2e-3)
+        report("spade_bwd dbeta  C%d xs%d" % (C, xs), nchw(dgb[..., bi].contiguous()), beta.grad, 2e-3)
+        report("bn_bwd dx        C%d xs%d" % (C, xs), nchw(dx), x.grad, 2e-5)
+    # ---- plain child-sum (upsample backward)
+    gch = torch.randn(2, 32, 16, 16, generator=g).to(dev)
+    ref = gch.view(2, 32, 8, 2, 8, 2).sum(dim=(3, 5))
+    dxs = ops.bn_bwd_apply(nhwc(gch), nhwc(ref), 1, None, None, None, 1)
+    report("upsample bwd (child sum)", nchw(dxs), ref, 1e-6)
+    # ---- instance norm + lrelu (+mask) backward
+    x = (torch.randn(3, 64, 17, 17, generator=g).to(dev) * 2 + 0.5).requires_grad_(True)
+    pm = (torch.rand(3, 17, 17, generator=g) > 0.3).float().to(dev)
+    y = F.leaky_relu(F.instance_norm(x), 0.2) * pm.unsqueeze(1)
+    dy = torch.randn(3, 64, 17, 17, generator=g).to(dev)
+    y.backward(dy)
+    yf, ss = ops.instance_norm_act_fwd(nhwc(x.detach()), 2, 1e-5, pmul=pm)
+    report("instance_norm_act_fwd", nchw(yf), y.detach(), 1e-5)
+    report("in_bwd", nchw(ops.in_bwd(nhwc(dy), nhwc(x.detach()), ss, 2, pmul=pm)), x.grad, 2e-5)
+    # ---- thin conv gradients
+    for (Cin, CinP, Cout, k, s_, p_, pmode) in ((4, 4, 128, 3, 1, 1, 0), (7, 8, 64, 4, 2, 2, 0), (3, 4, 64, 7, 1, 3, 1), (3, 4, 64, 3, 2, 1, 0)):
+        x = torch.randn(2, Cin, 32, 32, generator=g).to(dev).requires_grad_(True)
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / 6).to(dev).requires_grad_(True)
+        xp = F.pad(x, (p_,) * 4, mode="reflect") if pmode else x
+        y = F.conv2d(xp, w, None, stride=s_, padding=0 if pmode else p_)
+        dz = torch.randn(y.shape, generator=g).to(dev)
+        y.backward(dz)
+        dwt = ops.thin_wgrad(ops.nchw_to_nhwc(x.detach(), CinP), nhwc(dz), k, k, s_, p_, pad_mode=pmode)
+        dw = dwt.view(k, k, CinP, Cout).permute(3, 2, 0, 1)[:, :Cin]
+        torch.cuda.synchronize()
+        report("thin_wgrad %d->%d k%d s%d pm%d" % (Cin, Cout, k, s_, pmode), dw, w.grad, 2e-5)
+        if Cin == 7:
+            dimg = torch.zeros(2, 3, 32, 32, device=dev)
+            ops.thin_dgrad3(nhwc(dz), ops.pack_weight_thin(w.detach(), 8), dimg, k, k, s_, p_, 4)
+            report("thin_dgrad3 (image channels)", dimg, x.grad[:, 4:7], 2e-5)
+    # seg_resize variant of thin_wgrad (mlp_shared)
+    seg = torch.randn(2, 4, 64, 64, generator=g).to(dev)
+    w = (torch.randn(128, 4, 3, 3, generator=g) / 6).to(dev).requires_grad_(True)
+    y = F.conv2d(F.interpolate(seg, size=(16, 16), mode="nearest"), w, None, padding=1)
+    dz = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dz)
+    dwt = ops.thin_wgrad(nhwc(seg), nhwc(dz), 3, 3, 1, 1, seg_resize=4, in_hw=(16, 16))
+    report("thin_wgrad seg_resize", dwt.view(3, 3, 4, 128).permute(3, 2, 0, 1), w.grad, 2e-5)
+    # ---- conv_img backward
+    x = torch.randn(2, 64, 24, 40, generator=g).to(dev).requires_grad_(True)
+    w = (torch.randn(3, 64, 3, 3, generator=g) / 24).to(dev).requires_grad_(True)
+    b = torch.randn(3, generator=g).to(dev).requires_grad_(True)
+    y = torch.tanh(F.conv2d(F.leaky_relu(x, 0.2), w, b, padding=1))
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dy)
+    dx, dw, db = ops.conv_img_bwd(dy, y.detach().contiguous(), nhwc(x.detach()), w.detach())
+    torch.cuda.synchronize()
+    report("conv_img_bwd dx", nchw(dx), x.grad, 2e-5)
+    report("conv_img_bwd dw", dw, w.grad, 2e-5)
+    report("conv_img_bwd db", db, b.grad, 2e-5)
+    # ---- conv_to1 backward
+    x = torch.randn(2, 128, 18, 18, generator=g).to(dev).requires_grad_(True)
+    w = (torch.randn(1, 128, 4, 4, generator=g) / 45).to(dev).requires_grad_(True)
+    b = torch.randn(1, generator=g).to(dev).requires_grad_(True)
+    y = F.conv2d(x, w, b, padding=2)
+    dl = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dl)
+    dx, dw, db = ops.conv_to1_bwd(nhwc(dl), nhwc(x.detach()), w.detach(), 2)
+    torch.cuda.synchronize()
+    report("conv_to1_bwd dx", nchw(dx), x.grad, 2e-5)
+    report("conv_to1_bwd dw", dw, w.grad, 2e-5)
+    report("conv_to1_bwd db", db, b.grad, 2e-5)
+    # ---- avg-pool, reflect-pad, bilinear, masked-mean, blend backward
+    x = torch.randn(2, 8, 33, 31, generator=g).to(dev).requires_grad_(True)
+    y = F.avg_pool2d(x, 3, 2, [1, 1], count_include_pad=False)
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dy)
+    din = torch.zeros(2, 33, 31, 8, device=dev)
+    ops.avgpool3s2_bwd(nhwc(dy), din)
+    report("avgpool3s2_bwd", nchw(din), x.grad, 1e-5)
+    x = torch.randn(2, 32, 12, 14, generator=g).to(dev).requires_grad_(True)
+    y = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dy)
+    report("reflect_pad_bwd", nchw(ops.reflect_pad_bwd(nhwc(dy), 1)), x.grad, 1e-5)
+    x = torch.randn(2, 64, 16, 16, generator=g).to(dev).requires_grad_(True)
+    y = F.interpolate(x, size=(8, 8), mode="bilinear")
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dy)
+    report("resize_bilinear_bwd", nchw(ops.resize_bilinear_bwd(nhwc(dy), (16, 16))), x.grad, 1e-5)
+    x = torch.randn(2, 64, 4, 4, generator=g).to(dev).requires_grad_(True)
+    mref = (torch.rand(2, 64, 64, generator=g) > 0.5).float().to(dev)
+    mtag = (torch.rand(2, 64, 64, generator=g) > 0.5).float().to(dev)
+    lr = mref[:, ::16, ::16].unsqueeze(1); lt = mtag[:, ::16, ::16].unsqueeze(1)
+    y = ((x * lr).sum(dim=(2, 3), keepdim=True) / lr.sum(dim=(2, 3), keepdim=True).clamp(min=1)) * lt
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    y.backward(dy)
+    report("masked_mean_bcast_bwd", nchw(ops.masked_mean_bcast_bwd(nhwc(dy), mref, mtag)), x.grad, 1e-5)
+    dout = torch.randn(2, 32, 16, 16, generator=g).to(dev)
+    hair = (torch.rand(2, 64, 64, generator=g) > 0.5).float().to(dev)
+    back = (torch.rand(2, 64, 64, generator=g) > 0.5).float().to(dev)
+    dyb, dbf = ops.blend_bwd(nhwc(dout), hair, back, 4)
+    report("blend_bwd dy", nchw(dyb), dout * (1 - back[:, ::4, ::4].unsqueeze(1)), 1e-6)
+    report("blend_bwd dbf", nchw(dbf), dout * (1 - hair[:, ::4, ::4].unsqueeze(1)), 1e-6)
+    # ---- spectral norm backward
+    import torch.nn as nn
+    conv = nn.utils.spectral_norm(nn.Conv2d(64, 32, 3, padding=1)).to(dev)
+    conv.train()
+    xin = torch.randn(2, 64, 8, 8, generator=g).to(dev)
+    yy = conv(xin)
+    dyy = torch.randn(yy.shape, generator=g).to(dev)
+    yy.backward(dyy)
+    with torch.no_grad():
+        wmat = conv.weight_orig.reshape(32, -1)
+        sigma = torch.dot(conv.weight_u, wmat @ conv.weight_v)
+        wt = (conv.weight_orig / sigma).detach().requires_grad_(True)
+    F.conv2d(xin, wt, conv.bias.detach(), padding=1).backward(dyy)
+    inv = (1.0 / sigma).reshape(1).contiguous()
+    got = ops.spectral_norm_bwd(wt.grad.contiguous(), conv.weight_orig.detach(), conv.weight_u, conv.weight_v, inv)
+    report("spectral_norm_bwd", got, conv.weight_orig.grad, 2e-5)
+    # ---- gamma|beta packed dgrad operand + packed wgrad unpack
+    C = 64
+    actv = tf32_trunc(torch.randn(2, 128, 16, 16, generator=g).to(dev)).requires_grad_(True)
+    wg = tf32_trunc((torch.randn(C, 128, 3, 3, generator=g) / 34).to(dev)).requires_grad_(True)
+    wb = tf32_trunc((torch.randn(C, 128, 3, 3, generator=g) / 34).to(dev)).requires_grad_(True)
+    gam = F.conv2d(actv, wg, None, padding=1); bet = F.conv2d(actv, wb, None, padding=1)
+    dgam = tf32_trunc(torch.randn(gam.shape, generator=g).to(dev)); dbet = tf32_trunc(torch.randn(bet.shape, generator=g).to(dev))
+    (gam * dgam + bet * dbet).sum().backward()
+    bn = ops.spade_bn(C); half = bn // 2
+    ch = torch.arange(C, device=dev); gi = (ch // half) * bn + ch % half; bi = gi + half
+    dgb = torch.zeros(2, 16, 16, 2 * C, device=dev)
+    dgb[..., gi] = nhwc(dgam); dgb[..., bi] = nhwc(dbet)
+    dactv = ops.conv_igemm(dgb, ops.pack_weight_dgrad_gb(wg.detach(), wb.detach()), 128, 3, 3, 1, 1)
+    dwg, dwb = ops.unpack_wgrad_gb(ops.conv_wgrad(dgb, nhwc(actv.detach()), 3, 3, 1, 1), C, 128)
+    torch.cuda.synchronize()
+    report("gamma|beta dgrad (dactv)", nchw(dactv), actv.grad, 5e-5)
+    report("gamma|beta wgrad dWg", dwg, wg.grad, 5e-5)
+    report("gamma|beta wgrad dWb", dwb, wb.grad, 5e-5)
+
+
 def _time(fn, iters=5):
     for _ in range(2):
         fn()
