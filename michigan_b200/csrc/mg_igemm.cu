@@ -236,6 +236,24 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int tw = m % p.tiles_w;
             const int th = (m / p.tiles_w) % p.tiles_h;
             const int tn = m / m_tiles_per_img;
+            // per-tile pixel bookkeeping for the (up to 8) pixels this lane serves in the transposed domain
+            uint32_t pixo[8], srco[8], msko[8];
+            uint32_t vmask = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                pixo[j] = srco[j] = msko[j] = 0;
+                if (j >= passes) continue;
+                const int r = quarter * 32 + j * ppp + psub;
+                const int ow = tw * p.TW + (r & (p.TW - 1));
+                const int oh = th * p.TH + ((r >> twl) & (p.TH - 1));
+                const int n = tn * p.TN + (r >> (twl + thl));
+                if (ow >= p.OW || oh >= p.OH || n >= p.N) continue;
+                vmask |= 1u << j;
+                pixo[j] = (uint32_t)(((size_t)n * p.OHF + (size_t)oh * p.os + p.ooh) * p.OWF + (size_t)ow * p.os + p.oow);
+                if (spade) srco[j] = (uint32_t)(((size_t)n * p.XH + (oh >> p.x_shift)) * p.XW + (ow >> p.x_shift));
+                else if (p.res) srco[j] = (uint32_t)(((size_t)n * p.RH + (oh >> p.res_shift)) * p.RW + (ow >> p.res_shift));
+                if (p.bf) msko[j] = (uint32_t)(((size_t)n * p.MH + (size_t)oh * p.mask_stride) * p.MW + (size_t)ow * p.mask_stride);
+            }
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -275,17 +293,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (j >= passes) continue;
-                    const int r = quarter * 32 + j * ppp + psub;
-                    const int ow = tw * p.TW + (r & (p.TW - 1));
-                    const int oh = th * p.TH + ((r >> twl) & (p.TH - 1));
-                    const int n = tn * p.TN + (r >> (twl + thl));
-                    if (ow >= p.OW || oh >= p.OH || n >= p.N) continue;
-                    const size_t pix = ((size_t)n * p.OHF + (size_t)oh * p.os + p.ooh) * p.OWF + (size_t)ow * p.os + p.oow;
+                    if (!((vmask >> j) & 1u)) continue;
+                    const size_t pix = pixo[j];
                     float y[4];
                     if (spade) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(
-                            p.x + (((size_t)n * p.XH + (oh >> p.x_shift)) * p.XW + (ow >> p.x_shift)) * p.Cout + cch));
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)srco[j] * p.Cout + cch));
                         const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
                         if (p.aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + cch) = gs;
                         y[0] = fmaf(fmaf(xv.x, sc4.x, sh4.x), gs.x, bb4.x + bv[j].x);
@@ -299,14 +311,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         y[0] = fmaf(av[j].x, ps, bias4.x); y[1] = fmaf(av[j].y, ps, bias4.y);
                         y[2] = fmaf(av[j].z, ps, bias4.z); y[3] = fmaf(av[j].w, ps, bias4.w);
                         if (p.res) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4*>(
-                                p.res + (((size_t)n * p.RH + (oh >> p.res_shift)) * p.RW + (ow >> p.res_shift)) * p.Cout + cch));
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)srco[j] * p.Cout + cch));
                             y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], p.act);
                         if (p.bf) {
-                            const size_t mp = ((size_t)n * p.MH + (size_t)oh * p.mask_stride) * p.MW + (size_t)ow * p.mask_stride;
+                            const size_t mp = msko[j];
                             const float om_hair = 1.f - __ldg(p.hair + mp), om_back = 1.f - __ldg(p.back + mp);
                             const float4 bfv = __ldg(reinterpret_cast<const float4*>(p.bf + pix * p.Cout + cch));
                             y[0] = bfv.x * om_hair + y[0] * om_back; y[1] = bfv.y * om_hair + y[1] * om_back;
@@ -336,16 +347,17 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int i = 0; i < 2; ++i) {
                             const float a = y[2 * i], b = y[2 * i + 1];
                             if (p.out16_fmt == 1) {
-                                const __half ha = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
-                                const __half hb = __float2half_rn(fminf(fmaxf(b, -65504.f), 65504.f));
-                                hi[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-                                lo[i] = (uint32_t)__half_as_ushort(__float2half_rn(a - __half2float(ha))) |
-                                        ((uint32_t)__half_as_ushort(__float2half_rn(b - __half2float(hb))) << 16);
+                                const __half2 h2 = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+                                const float2 hf = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+                                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
                             } else {
-                                const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-                                hi[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-                                lo[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a - __bfloat162float(ha))) |
-                                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b - __bfloat162float(hb))) << 16);
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                const float2 hf = __bfloat1622float2(h2);
+                                const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
                             }
                         }
                         const size_t eo = pix * p.Cout + cch;
