@@ -112,7 +112,7 @@ int mg_pack_weight_gb(const float* wg_oihw, const float* wb_oihw, float* wpack, 
 int mg_pack_weight16(const float* w_oihw, void* out, int O, int I, int KH, int KW, const float* inv_sigma, int fmt,
                      int split, void* stream);
 int mg_pack_weight_gb16(const float* wg_oihw, const float* wb_oihw, void* out, int C, int I, int KH, int KW, int BN,
-                        int fmt, void* stream);
+                        int fmt, int split, void* stream);
 
 /* Thin direct convolutions on CUDA cores (exact fp32): layers whose Cin is 3/4/7.
  * mode 0: zero padding; mode 1: reflection padding (MaskGAN_networks.py:120-121);

@@ -60,7 +60,7 @@ SIGNATURES = {
     "mg_pack_weight": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
     "mg_pack_weight_gb": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_pack_weight16": [_p, _p, _i, _i, _i, _i, _p, _i, _i, _p],
-    "mg_pack_weight_gb16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_pack_weight_gb16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_thin": [C.POINTER(ThinArgs), _p],
     "mg_pack_weight_thin": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_conv_img": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],

@@ -92,7 +92,7 @@ __global__ void pack_weight16_kernel(const float* __restrict__ w, uint16_t* __re
     }
 }
 __global__ void pack_weight_gb16_kernel(const float* __restrict__ wg, const float* __restrict__ wb, uint16_t* __restrict__ out,
-                                        int C, int I, int KH, int KW, int BN, int fmt) {
+                                        int C, int I, int KH, int KW, int BN, int fmt, int split) {
     const long long total = 2LL * C * KH * KW * I;
     const int half = BN / 2;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -107,7 +107,13 @@ __global__ void pack_weight_gb16_kernel(const float* __restrict__ wg, const floa
         const int c = tile * half + (rr < half ? rr : rr - half);
         uint16_t hi, lo;
         split16(src[(((long long)c * I + i) * KH + kh) * KW + kw], fmt, hi, lo);
-        out[idx] = hi;
+        if (!split) {
+            out[idx] = hi;
+        } else {
+            const size_t base = ((size_t)R * KH * KW + (size_t)(kh * KW + kw)) * 2 * I;
+            out[base + i] = hi;
+            out[base + I + i] = lo;
+        }
     }
 }
 
@@ -127,8 +133,8 @@ __global__ void pack_weight_thin_kernel(const float* __restrict__ w, float* __re
 
 // ------------------------------------------------------------------------------------ thin direct conv
 // Block = 8 warps; output tile 8 rows x 16 cols; warp w owns row w, lane owns CPL output channels.
-template <int CINP, int CPL>
-__global__ void __launch_bounds__(256)
+template <int CINP, int CPL, int KS>
+__global__ void __launch_bounds__(256, 2)
 thin_conv_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) {
     extern __shared__ __align__(16) float sm[];
     const int KH = a.KH, KW = a.KW, s = a.stride;
@@ -178,54 +184,61 @@ thin_conv_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) 
         __syncthreads();
 
         const int oh = oh0 + warp;
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-            float acc[8][CPL];
+        // 16 pixels (one tile row) x CPL channels per lane; weights of a tap are loaded once for all 16 pixels
+        float acc[16][CPL];
 #pragma unroll
-            for (int p_ = 0; p_ < 8; ++p_)
+        for (int p_ = 0; p_ < 16; ++p_)
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) acc[p_][c] = 0.f;
-            if (lane_active) {
-                for (int kh = 0; kh < KH; ++kh) {
-                    const float* row = in_s + (size_t)((warp * s + kh) * PW) * CINP;
-                    for (int kw = 0; kw < KW; ++kw) {
-                        const float* wt = w_s + (size_t)((kh * KW + kw) * CINP) * Cout + c_base;
-                        float wv[CINP][CPL];
+            for (int c = 0; c < CPL; ++c) acc[p_][c] = 0.f;
+        if (lane_active) {
+            auto tap = [&](int kh, int kw) {
+                const float* row = in_s + (size_t)((warp * s + kh) * PW) * CINP;
+                const float* wt = w_s + (size_t)((kh * KW + kw) * CINP) * Cout + c_base;
+                float wv[CINP][CPL];
 #pragma unroll
-                        for (int ci = 0; ci < CINP; ++ci) {
-                            if constexpr (CPL == 4) {
-                                const float4 t = *reinterpret_cast<const float4*>(wt + (size_t)ci * Cout);
-                                wv[ci][0] = t.x; wv[ci][1] = t.y; wv[ci][2] = t.z; wv[ci][3] = t.w;
-                            } else {
-                                const float2 t = *reinterpret_cast<const float2*>(wt + (size_t)ci * Cout);
-                                wv[ci][0] = t.x; wv[ci][1] = t.y;
-                            }
-                        }
-#pragma unroll
-                        for (int p_ = 0; p_ < 8; ++p_) {
-                            const float* ip = row + (size_t)(((g * 8 + p_) * s + kw)) * CINP;
-                            float iv[CINP];
-                            const float4 t0 = *reinterpret_cast<const float4*>(ip);
-                            iv[0] = t0.x; iv[1] = t0.y; iv[2] = t0.z; iv[3] = t0.w;
-                            if constexpr (CINP == 8) {
-                                const float4 t1 = *reinterpret_cast<const float4*>(ip + 4);
-                                iv[4] = t1.x; iv[5] = t1.y; iv[6] = t1.z; iv[7] = t1.w;
-                            }
-#pragma unroll
-                            for (int ci = 0; ci < CINP; ++ci)
-#pragma unroll
-                                for (int c = 0; c < CPL; ++c) acc[p_][c] = fmaf(iv[ci], wv[ci][c], acc[p_][c]);
-                        }
+                for (int ci = 0; ci < CINP; ++ci) {
+                    if constexpr (CPL == 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(wt + (size_t)ci * Cout);
+                        wv[ci][0] = t.x; wv[ci][1] = t.y; wv[ci][2] = t.z; wv[ci][3] = t.w;
+                    } else {
+                        const float2 t = *reinterpret_cast<const float2*>(wt + (size_t)ci * Cout);
+                        wv[ci][0] = t.x; wv[ci][1] = t.y;
                     }
                 }
+#pragma unroll
+                for (int p_ = 0; p_ < 16; ++p_) {
+                    const float* ip = row + (size_t)((p_ * s + kw)) * CINP;
+                    float iv[CINP];
+                    const float4 t0 = *reinterpret_cast<const float4*>(ip);
+                    iv[0] = t0.x; iv[1] = t0.y; iv[2] = t0.z; iv[3] = t0.w;
+                    if constexpr (CINP == 8) {
+                        const float4 t1 = *reinterpret_cast<const float4*>(ip + 4);
+                        iv[4] = t1.x; iv[5] = t1.y; iv[6] = t1.z; iv[7] = t1.w;
+                    }
+#pragma unroll
+                    for (int ci = 0; ci < CINP; ++ci)
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) acc[p_][c] = fmaf(iv[ci], wv[ci][c], acc[p_][c]);
+                }
+            };
+            if constexpr (KS == 3) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) tap(kh, kw);
+            } else {
+                for (int kh = 0; kh < KH; ++kh)
+                    for (int kw = 0; kw < KW; ++kw) tap(kh, kw);
             }
+        }
+        {
             if (lane_active && oh < a.OH) {
                 float bv[CPL];
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) bv[c] = a.bias ? __ldg(a.bias + c_base + c) : 0.f;
 #pragma unroll
-                for (int p_ = 0; p_ < 8; ++p_) {
-                    const int ow = ow0 + g * 8 + p_;
+                for (int p_ = 0; p_ < 16; ++p_) {
+                    const int ow = ow0 + p_;
                     if (ow >= a.OW) continue;
                     const size_t pix = ((size_t)n * a.OH + oh) * a.OW + ow;
                     const float ps = a.pscale ? __ldg(a.pscale + pix) : 1.f;
@@ -792,17 +805,18 @@ extern "C" int mg_conv_thin(const mg_thin_args* a, void* stream) {
     if (smem > 200 * 1024) return set_error(-5, "mg_conv_thin: smem %zu too large", smem);
     int grid = num_sms() * 2;
     if (grid > num_tiles) grid = num_tiles;
-#define LAUNCH_THIN(CI, CP)                                                                                  \
+#define LAUNCH_THIN(CI, CP, KS_)                                                                             \
     do {                                                                                                     \
-        cudaError_t e = cudaFuncSetAttribute(thin_conv_kernel<CI, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        cudaError_t e = cudaFuncSetAttribute(thin_conv_kernel<CI, CP, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              200 * 1024);                                                    \
         if (e != cudaSuccess) return set_error((int)e, "thin attr: %s", cudaGetErrorString(e));              \
-        thin_conv_kernel<CI, CP><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);          \
+        thin_conv_kernel<CI, CP, KS_><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);     \
     } while (0)
-    if (a->CinP == 4 && cpl == 4) LAUNCH_THIN(4, 4);
-    else if (a->CinP == 4) LAUNCH_THIN(4, 2);
-    else if (cpl == 4) LAUNCH_THIN(8, 4);
-    else LAUNCH_THIN(8, 2);
+    const bool k3 = a->KH == 3 && a->KW == 3;
+    if (a->CinP == 4 && cpl == 4) { if (k3) LAUNCH_THIN(4, 4, 3); else LAUNCH_THIN(4, 4, 0); }
+    else if (a->CinP == 4) { if (k3) LAUNCH_THIN(4, 2, 3); else LAUNCH_THIN(4, 2, 0); }
+    else if (cpl == 4) LAUNCH_THIN(8, 4, 0);
+    else LAUNCH_THIN(8, 2, 0);
     return check_launch("mg_conv_thin");
 }
 
@@ -1107,9 +1121,9 @@ extern "C" int mg_pack_weight16(const float* w, void* out, int O, int I, int KH,
     return check_launch("mg_pack_weight16");
 }
 extern "C" int mg_pack_weight_gb16(const float* wg, const float* wb, void* out, int C, int I, int KH, int KW, int BN, int fmt,
-                                   void* stream) {
+                                   int split, void* stream) {
     if (!wg || !wb || !out) return set_error(-1, "mg_pack_weight_gb16: null pointer");
     if (BN % 64 != 0 || (2 * C) % BN != 0) return set_error(-2, "mg_pack_weight_gb16: bad BN %d for C %d", BN, C);
-    pack_weight_gb16_kernel<<<ew_grid(2LL * C * I * KH * KW), 256, 0, ST(stream)>>>(wg, wb, (uint16_t*)out, C, I, KH, KW, BN, fmt);
+    pack_weight_gb16_kernel<<<ew_grid(2LL * C * I * KH * KW), 256, 0, ST(stream)>>>(wg, wb, (uint16_t*)out, C, I, KH, KW, BN, fmt, split);
     return check_launch("mg_pack_weight_gb16");
 }

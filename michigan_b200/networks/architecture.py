@@ -61,16 +61,15 @@ class SPADEResnetBlock(nn.Module):
         fmt = precision.conv_fmt(conv.weight.shape[1])
         return self._cache.get((name, fmt), [conv.weight], lambda: precision.pack_conv(conv.weight.detach(), None, fmt))
 
-    def _spade_pack(self, name):
+    def _spade_pack(self, name, gfmt, gsplit):
         sp = getattr(self, name)
         c = self._cache
-        gfmt = precision.gb_fmt()
         if gfmt == ops.TF32:
             wgb = c.get(name + ".gb", [sp.mlp_gamma.weight, sp.mlp_beta.weight],
                         lambda: ops.pack_weight_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach()))
         else:
-            wgb = c.get(name + ".gb16", [sp.mlp_gamma.weight, sp.mlp_beta.weight],
-                        lambda: ops.pack_weight_gb16(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach(), gfmt))
+            wgb = c.get((name + ".gb16", gfmt, gsplit), [sp.mlp_gamma.weight, sp.mlp_beta.weight],
+                        lambda: ops.pack_weight_gb16(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach(), gfmt, gsplit))
         wsh = c.get(name + ".sh", [sp.mlp_shared[0].weight],
                     lambda: ops.pack_weight_thin(sp.mlp_shared[0].weight.detach(), 4))
         g1 = c.get(name + ".g1", [sp.mlp_gamma.bias], lambda: (sp.mlp_gamma.bias.detach() + 1.0).contiguous())
@@ -94,13 +93,13 @@ class SPADEResnetBlock(nn.Module):
             if self.learned_shortcut:
                 nss, nhs = self.norm_s.param_free_norm.scale_shift(x)
 
-        gfmt = precision.gb_fmt()
+        gfmt, gsplit = precision.gb_policy(h)
 
         def spade_act(name, src, shift, nscale, nshift, act):
-            cfmt = precision.conv_fmt(src.shape[-1])
             """-> tensor-core operand (fmt, hi, lo) holding act(SPADE(src)) for the consumer conv."""
-            wsh, bsh, wgb, g1, bb = self._spade_pack(name)
-            kw_a, get_a = precision.out_spec(gfmt, False)
+            cfmt = precision.conv_fmt(src.shape[-1])
+            wsh, bsh, wgb, g1, bb = self._spade_pack(name, gfmt, gsplit)
+            kw_a, get_a = precision.out_spec(gfmt, gsplit)
             actv = get_a(ops.conv_thin(seg4, wsh, bsh, 128, 3, 3, 1, 1, seg_resize=R, act=ops.ACT_RELU, out_hw=(h, w), **kw_a))
             c = src.shape[-1]
             kw_h, get_h = precision.out_spec(cfmt, cfmt == ops.BF16)

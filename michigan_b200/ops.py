@@ -87,11 +87,11 @@ def pack_weight16(w_oihw, inv_sigma=None, fmt=BF16, split=True):
     return out
 
 
-def pack_weight_gb16(wg, wb, fmt=F16):
+def pack_weight_gb16(wg, wb, fmt=F16, split=False):
     _chk(wg, "wg"); _chk(wb, "wb")
     Cc, I, KH, KW = wg.shape
-    out = torch.empty((2 * Cc, KH * KW * I), device=wg.device, dtype=_T16[fmt])
-    check(_lib.load().mg_pack_weight_gb16(_p(wg), _p(wb), _p(out), Cc, I, KH, KW, spade_bn(Cc), fmt, _stream()),
+    out = torch.empty((2 * Cc, KH * KW * I * (2 if split else 1)), device=wg.device, dtype=_T16[fmt])
+    check(_lib.load().mg_pack_weight_gb16(_p(wg), _p(wb), _p(out), Cc, I, KH, KW, spade_bn(Cc), fmt, int(split), _stream()),
           "mg_pack_weight_gb16")
     return out
 

@@ -36,6 +36,16 @@ def gb_fmt(cin=128):
     return ops.F16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
 
 
+def gb_policy(h):
+    """(fmt, split) of the SPADE gamma/beta GEMM at feature height h.  The low-resolution blocks
+    (head_0, G_middle_0/1, up_0: h <= 64, 6 % of the gamma/beta FLOPs) feed every later batch-norm, so
+    their GEMMs use the three-pass bf16 split; emulation on the 512x512 net: image max-abs error
+    1.0e-3 -> 4.9e-4."""
+    if _mode != "mixed16":
+        return ops.TF32, False
+    return (ops.BF16, True) if h <= 64 else (ops.F16, False)
+
+
 def conv_fmt(cin):
     """Operand format of the split-precision convs (BF16 -> three passes) or TF32 (one pass)."""
     return ops.BF16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
