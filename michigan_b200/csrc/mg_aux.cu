@@ -133,8 +133,8 @@ __global__ void pack_weight_thin_kernel(const float* __restrict__ w, float* __re
 
 // ------------------------------------------------------------------------------------ thin direct conv
 // Block = 8 warps; output tile 8 rows x 16 cols; warp w owns row w, lane owns CPL output channels.
-template <int CINP, int CPL, int KS>
-__global__ void __launch_bounds__(256, 2)
+template <int CINP, int CPL>
+__global__ void __launch_bounds__(256)
 thin_conv_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) {
     extern __shared__ __align__(16) float sm[];
     const int KH = a.KH, KW = a.KW, s = a.stride;
@@ -184,61 +184,54 @@ thin_conv_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) 
         __syncthreads();
 
         const int oh = oh0 + warp;
-        // 16 pixels (one tile row) x CPL channels per lane; weights of a tap are loaded once for all 16 pixels
-        float acc[16][CPL];
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            float acc[8][CPL];
 #pragma unroll
-        for (int p_ = 0; p_ < 16; ++p_)
+            for (int p_ = 0; p_ < 8; ++p_)
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[p_][c] = 0.f;
-        if (lane_active) {
-            auto tap = [&](int kh, int kw) {
-                const float* row = in_s + (size_t)((warp * s + kh) * PW) * CINP;
-                const float* wt = w_s + (size_t)((kh * KW + kw) * CINP) * Cout + c_base;
-                float wv[CINP][CPL];
+                for (int c = 0; c < CPL; ++c) acc[p_][c] = 0.f;
+            if (lane_active) {
+                for (int kh = 0; kh < KH; ++kh) {
+                    const float* row = in_s + (size_t)((warp * s + kh) * PW) * CINP;
+                    for (int kw = 0; kw < KW; ++kw) {
+                        const float* wt = w_s + (size_t)((kh * KW + kw) * CINP) * Cout + c_base;
+                        float wv[CINP][CPL];
 #pragma unroll
-                for (int ci = 0; ci < CINP; ++ci) {
-                    if constexpr (CPL == 4) {
-                        const float4 t = *reinterpret_cast<const float4*>(wt + (size_t)ci * Cout);
-                        wv[ci][0] = t.x; wv[ci][1] = t.y; wv[ci][2] = t.z; wv[ci][3] = t.w;
-                    } else {
-                        const float2 t = *reinterpret_cast<const float2*>(wt + (size_t)ci * Cout);
-                        wv[ci][0] = t.x; wv[ci][1] = t.y;
+                        for (int ci = 0; ci < CINP; ++ci) {
+                            if constexpr (CPL == 4) {
+                                const float4 t = *reinterpret_cast<const float4*>(wt + (size_t)ci * Cout);
+                                wv[ci][0] = t.x; wv[ci][1] = t.y; wv[ci][2] = t.z; wv[ci][3] = t.w;
+                            } else {
+                                const float2 t = *reinterpret_cast<const float2*>(wt + (size_t)ci * Cout);
+                                wv[ci][0] = t.x; wv[ci][1] = t.y;
+                            }
+                        }
+#pragma unroll
+                        for (int p_ = 0; p_ < 8; ++p_) {
+                            const float* ip = row + (size_t)(((g * 8 + p_) * s + kw)) * CINP;
+                            float iv[CINP];
+                            const float4 t0 = *reinterpret_cast<const float4*>(ip);
+                            iv[0] = t0.x; iv[1] = t0.y; iv[2] = t0.z; iv[3] = t0.w;
+                            if constexpr (CINP == 8) {
+                                const float4 t1 = *reinterpret_cast<const float4*>(ip + 4);
+                                iv[4] = t1.x; iv[5] = t1.y; iv[6] = t1.z; iv[7] = t1.w;
+                            }
+#pragma unroll
+                            for (int ci = 0; ci < CINP; ++ci)
+#pragma unroll
+                                for (int c = 0; c < CPL; ++c) acc[p_][c] = fmaf(iv[ci], wv[ci][c], acc[p_][c]);
+                        }
                     }
                 }
-#pragma unroll
-                for (int p_ = 0; p_ < 16; ++p_) {
-                    const float* ip = row + (size_t)((p_ * s + kw)) * CINP;
-                    float iv[CINP];
-                    const float4 t0 = *reinterpret_cast<const float4*>(ip);
-                    iv[0] = t0.x; iv[1] = t0.y; iv[2] = t0.z; iv[3] = t0.w;
-                    if constexpr (CINP == 8) {
-                        const float4 t1 = *reinterpret_cast<const float4*>(ip + 4);
-                        iv[4] = t1.x; iv[5] = t1.y; iv[6] = t1.z; iv[7] = t1.w;
-                    }
-#pragma unroll
-                    for (int ci = 0; ci < CINP; ++ci)
-#pragma unroll
-                        for (int c = 0; c < CPL; ++c) acc[p_][c] = fmaf(iv[ci], wv[ci][c], acc[p_][c]);
-                }
-            };
-            if constexpr (KS == 3) {
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) tap(kh, kw);
-            } else {
-                for (int kh = 0; kh < KH; ++kh)
-                    for (int kw = 0; kw < KW; ++kw) tap(kh, kw);
             }
-        }
-        {
             if (lane_active && oh < a.OH) {
                 float bv[CPL];
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) bv[c] = a.bias ? __ldg(a.bias + c_base + c) : 0.f;
 #pragma unroll
-                for (int p_ = 0; p_ < 16; ++p_) {
-                    const int ow = ow0 + p_;
+                for (int p_ = 0; p_ < 8; ++p_) {
+                    const int ow = ow0 + g * 8 + p_;
                     if (ow >= a.OW) continue;
                     const size_t pix = ((size_t)n * a.OH + oh) * a.OW + ow;
                     const float ps = a.pscale ? __ldg(a.pscale + pix) : 1.f;
@@ -805,18 +798,17 @@ extern "C" int mg_conv_thin(const mg_thin_args* a, void* stream) {
     if (smem > 200 * 1024) return set_error(-5, "mg_conv_thin: smem %zu too large", smem);
     int grid = num_sms() * 2;
     if (grid > num_tiles) grid = num_tiles;
-#define LAUNCH_THIN(CI, CP, KS_)                                                                             \
+#define LAUNCH_THIN(CI, CP)                                                                                  \
     do {                                                                                                     \
-        cudaError_t e = cudaFuncSetAttribute(thin_conv_kernel<CI, CP, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        cudaError_t e = cudaFuncSetAttribute(thin_conv_kernel<CI, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              200 * 1024);                                                    \
         if (e != cudaSuccess) return set_error((int)e, "thin attr: %s", cudaGetErrorString(e));              \
-        thin_conv_kernel<CI, CP, KS_><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);     \
+        thin_conv_kernel<CI, CP><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);          \
     } while (0)
-    const bool k3 = a->KH == 3 && a->KW == 3;
-    if (a->CinP == 4 && cpl == 4) { if (k3) LAUNCH_THIN(4, 4, 3); else LAUNCH_THIN(4, 4, 0); }
-    else if (a->CinP == 4) { if (k3) LAUNCH_THIN(4, 2, 3); else LAUNCH_THIN(4, 2, 0); }
-    else if (cpl == 4) LAUNCH_THIN(8, 4, 0);
-    else LAUNCH_THIN(8, 2, 0);
+    if (a->CinP == 4 && cpl == 4) LAUNCH_THIN(4, 4);
+    else if (a->CinP == 4) LAUNCH_THIN(4, 2);
+    else if (cpl == 4) LAUNCH_THIN(8, 4);
+    else LAUNCH_THIN(8, 2);
     return check_launch("mg_conv_thin");
 }
 

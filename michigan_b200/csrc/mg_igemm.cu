@@ -100,6 +100,10 @@ __device__ __forceinline__ void store16(const IgemmParams& p, const float (&y)[1
     }
 }
 
+// SPEC selects a compile-time specialisation of the (instruction-bound) epilogue:
+//   0 generic (everything decided at run time)
+//   1 SPADE + LeakyReLU -> bf16 hi/lo operand only      2 SPADE + no activation -> bf16 hi/lo operand only
+template <int SPEC>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
@@ -220,7 +224,15 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int quarter = warp & 3;
         const int half = ew >> 2;
         float* scr = reinterpret_cast<float*>(smem + p.epi_off) + ew * (32 * 36);
-        const bool spade = p.epi == 1;
+        constexpr bool kS = SPEC == 1 || SPEC == 2;
+        const bool spade = kS ? true : (p.epi == 1);
+        const int act = SPEC == 1 ? 2 : (SPEC == 2 ? 0 : p.act);
+        const bool has_out = kS ? false : (p.out != nullptr);
+        const bool has_hi = kS ? true : (p.out_hi != nullptr);
+        const bool has_lo = kS ? true : (p.out_lo != nullptr);
+        const int fmt16 = kS ? 2 : p.out16_fmt;
+        const bool has_aux = kS ? false : (p.aux != nullptr);
+        const bool do_round = kS ? false : (p.round_out != 0);
         const int span = spade ? (p.BN >> 2) : (p.BN >> 1);   // channels this warp owns per tile
         const int cw = (span % 32 == 0 && !p.epi_cw16) ? 32 : 16;
         const int rs = cw + 4;
@@ -299,13 +311,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (spade) {
                         const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)srco[j] * p.Cout + cch));
                         const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
-                        if (p.aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + cch) = gs;
+                        if (has_aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + cch) = gs;
                         y[0] = fmaf(fmaf(xv.x, sc4.x, sh4.x), gs.x, bb4.x + bv[j].x);
                         y[1] = fmaf(fmaf(xv.y, sc4.y, sh4.y), gs.y, bb4.y + bv[j].y);
                         y[2] = fmaf(fmaf(xv.z, sc4.z, sh4.z), gs.z, bb4.z + bv[j].z);
                         y[3] = fmaf(fmaf(xv.w, sc4.w, sh4.w), gs.w, bb4.w + bv[j].w);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], p.act);
+                        for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], act);
                     } else {
                         const float ps = p.pscale ? __ldg(p.pscale + pix) : 1.f;
                         y[0] = fmaf(av[j].x, ps, bias4.x); y[1] = fmaf(av[j].y, ps, bias4.y);
@@ -315,7 +327,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
                         }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], p.act);
+                        for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], act);
                         if (p.bf) {
                             const size_t mp = msko[j];
                             const float om_hair = 1.f - __ldg(p.hair + mp), om_back = 1.f - __ldg(p.back + mp);
@@ -329,11 +341,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             for (int i = 0; i < 4; ++i) y[i] *= pm;
                         }
                     }
-                    if (p.round_out) {
+                    if (do_round) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) y[i] = round_tf32(y[i]);
                     }
-                    if (p.out) {
+                    if (has_out) {
                         float4* op = reinterpret_cast<float4*>(p.out + pix * p.Cout + cch);
                         if (p.accumulate) {
                             const float4 o = *op;
@@ -341,12 +353,12 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         *op = make_float4(y[0], y[1], y[2], y[3]);
                     }
-                    if (p.out_hi) {
+                    if (has_hi) {
                         uint32_t hi[2], lo[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             const float a = y[2 * i], b = y[2 * i + 1];
-                            if (p.out16_fmt == 1) {
+                            if (fmt16 == 1) {
                                 const __half2 h2 = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
                                 const float2 hf = __half22float2(h2);
                                 const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -362,7 +374,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         const size_t eo = pix * p.Cout + cch;
                         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_hi) + eo) = make_uint2(hi[0], hi[1]);
-                        if (p.out_lo) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + eo) = make_uint2(lo[0], lo[1]);
+                        if (has_lo) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + eo) = make_uint2(lo[0], lo[1]);
                     }
                 }
             }
@@ -589,6 +601,8 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * 36 * 4 : 0;
     int stages = (227 * 1024 - 1024 - 512 - scratch_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
+    static const int stages_cap = getenv("MG_STAGES") ? atoi(getenv("MG_STAGES")) : 0;
+    if (stages_cap > 0 && stages > stages_cap) stages = stages_cap;
     p.stages = stages;
     p.epi_off = stages * stage_bytes + 512;
     p.idesc = a->a_fmt == 0 ? umma_idesc_tf32(128, BN) : umma_idesc_16(128, BN, a->a_fmt);
@@ -634,14 +648,22 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_set_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(igemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set_dev = dev;
     }
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    igemm_tf32_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
+    int spec = 0;
+    if (p.epi_impl == 1 && a->epi == MG_EPI_SPADE && !a->out && a->out_hi && a->out_lo && a->out16_fmt == 2 && !a->aux_out &&
+        !a->round_out && (a->act == MG_ACT_LRELU || a->act == MG_ACT_NONE))
+        spec = a->act == MG_ACT_LRELU ? 1 : 2;
+    if (spec == 1) igemm_tf32_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
+    else if (spec == 2) igemm_tf32_kernel<2><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
+    else igemm_tf32_kernel<0><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, "igemm launch: %s", cudaGetErrorString(e));

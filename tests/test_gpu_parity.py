@@ -216,10 +216,11 @@ def test_backward_chain_smooth_loss_vs_oracle():
     loss_o.backward()
     print("smooth loss: cuda %.6f oracle %.6f" % (float(loss), float(loss_o)))
     assert abs(float(loss) - float(loss_o)) <= 2e-3 * abs(float(loss_o))
+    failures = []
     for label, net, sd, names in (("G", G, sdG, names_G), ("D", D, sdD, names_D)):
         named = dict(net.named_parameters())
         gmax = max(sd[n].grad.norm().item() for n in names if sd[n].grad is not None)
-        worst, worst_name = 0.0, ""
+        rows = []
         for n in names:
             ref = sd[n].grad
             got = named[n].grad
@@ -227,11 +228,15 @@ def test_backward_chain_smooth_loss_vs_oracle():
                 assert got is None or float(got.abs().max()) == 0.0, n
                 continue
             assert got is not None, n
-            err = (got.cpu() - ref).norm().item() / max(ref.norm().item(), 1e-4 * gmax)
-            if err > worst:
-                worst, worst_name = err, n
-        print("   %s: worst relative L2 gradient error %.3e (%s)" % (label, worst, worst_name))
-        assert worst <= 3e-2, (label, worst_name, worst)
+            # 1-D tensors (biases) are sums with heavy cancellation: floor their scale at 1 % of the largest gradient
+            floor = (1e-2 if ref.dim() == 1 else 1e-4) * gmax
+            rows.append(((got.cpu() - ref).norm().item() / max(ref.norm().item(), floor), n, ref.norm().item()))
+        rows.sort(reverse=True)
+        print("   %s: largest relative L2 gradient errors (gmax %.3e):" % (label, gmax))
+        for e, n, rn in rows[:6]:
+            print("      %-50s err %.3e  |ref| %.3e" % (n, e, rn))
+        failures += [(label, n, e) for e, n, rn in rows if e > 3e-2]
+    assert not failures, failures[:10]
 
 
 def test_train_iteration_losses_and_grads_vs_golden():
