@@ -233,6 +233,34 @@ def main():
     for n in dnames:
         out["d_grad/" + n] = summary(gradsD[n], stride=53)
 
+    # ------------------------------------------------------------------ D step from the INITIAL weights
+    # (decoupled from the generator's Adam update, whose first step is sign-like and amplifies noise)
+    print("[D step from initial weights]")
+    netG.load_state_dict(sdG0)
+    netD.load_state_dict(sdD0)
+    random.seed(c["py_seed"] + 2)
+    k3 = rng_k(size, c["py_seed"] + 2)
+    random.seed(c["py_seed"] + 2)
+    trainer.run_discriminator_one_step(dict(data))
+    d0_losses = {kk: float(v.mean()) for kk, v in trainer.d_losses.items()}
+    gradsD0 = {n: p.grad.detach().clone() for n, p in netD.named_parameters() if p.grad is not None}
+    sdG_s3 = {kk: v.clone() for kk, v in sdG0.items()}
+    sdD_s3 = {kk: v.clone() for kk, v in sdD0.items()}
+    for n in dnames:
+        sdD_s3[n].requires_grad_(True)
+    dl3 = orc.compute_discriminator_loss(sdG_s3, sdD_s3, oopt, pre, rng_k=k3)
+    orc.trainer_loss(dl3).backward()
+    for kk in d0_losses:
+        print("  D loss %-10s ref %.6f oracle %.6f" % (kk, d0_losses[kk], float(dl3[kk].mean())))
+        assert abs(d0_losses[kk] - float(dl3[kk].mean())) <= 2e-5 * max(1.0, abs(d0_losses[kk]))
+    worst = max((gradsD0[n] - sdD_s3[n].grad).norm().item() / max(gradsD0[n].norm().item(), 1e-5) for n in dnames)
+    print("  D grads (initial weights): worst relative L2 error %.2e" % worst)
+    assert worst < 2e-2, worst
+    out["rng_k3"] = np.array([k3])
+    out["d0_losses"] = np.array([d0_losses["D_Fake"], d0_losses["D_real"]], dtype=np.float64)
+    for n in dnames:
+        out["d0_grad/" + n] = summary(gradsD0[n], stride=53)
+
     path = os.path.join(HERE, "golden_ngf64_128.npz")
     np.savez_compressed(path, **out)
     print("wrote %s (%.1f KB, %d arrays)" % (path, os.path.getsize(path) / 1024, len(out)))
