@@ -270,6 +270,10 @@ int mg_spectral_norm_bwd(const float* dwt, const float* w_orig, const float* u, 
 int mg_pack_weight_dgrad_gb(const float* wg, const float* wb, float* out, int C, int I, int BN, void* stream);
 int mg_unpack_wgrad_gb(const float* dw_packed, float* dwg, float* dwb, int C, int I, int BN, int accumulate, void* stream);
 
+/* [N,H,W,CinP] (CinP 4|8; H,W = size after the optional nearest down-sampling by seg_resize) -> TF32-rounded
+ * [N,H+2p,W+2p,32] with zero channel padding and reflection padding p: operand of mg_conv_wgrad for the thin convs. */
+int mg_pad_channels32(const float* in, float* out, int N, int H, int W, int CinP, int seg_resize, int reflect_pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mg_pack_weight_dgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "mg_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_conv_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_pad_channels32": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "mg_spade_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p],
     "mg_bn_bwd_apply": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _d, _p, _i, _p],
     "mg_blend_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cmath>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "mg_internal.h"
@@ -260,6 +261,131 @@ thin_conv_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) 
                             *reinterpret_cast<uint32_t*>(oh) = hi[0] | ((uint32_t)hi[1] << 16);
                             if (ol) *reinterpret_cast<uint32_t*>(ol) = lo[0] | ((uint32_t)lo[1] << 16);
                         }
+                    }
+                }
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------ thin conv, register-tiled
+// Same contract as thin_conv_kernel, for Cout = 16*CPT (64 or 128): SGEMM-style register tiling, each thread owns
+// 8 consecutive pixels of a tile row x CPT channels (tile = 8 rows x 16 cols of pixels, 256 threads = 16 pixel
+// groups x 16 channel groups).  Per tap and 4 input channels a thread issues 8 + CPT/ (4/4) shared loads for
+// 32*CPT FMAs, i.e. it is FMA-bound rather than LDS-bound.
+template <int CINP, int CPT>
+__global__ void __launch_bounds__(256, 1)
+thin_gemm_kernel(const mg_thin_args a, int tiles_w, int tiles_h, int num_tiles) {
+    extern __shared__ __align__(16) float sm[];
+    const int KH = a.KH, KW = a.KW, s = a.stride;
+    constexpr int Cout = 16 * CPT;
+    const int PH = 7 * s + KH, PW = 15 * s + KW;
+    float* w_s = sm;                               // [KH*KW][CINP][Cout]
+    float* in_s = sm + KH * KW * CINP * Cout;      // [PH][PW][CINP]
+    const int nw = KH * KW * CINP * Cout;
+    for (int i = threadIdx.x * 4; i < nw; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(a.w + i));
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int prow = ty >> 1, pcol0 = (ty & 1) * 8;
+    const int c_base = tx * CPT;
+    const int R = a.seg_resize > 0 ? a.seg_resize : 1;
+    const int IH = a.H, IW = a.W;
+    float bv[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) bv[c] = a.bias ? __ldg(a.bias + c_base + c) : 0.f;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int n = tile / (tiles_w * tiles_h);
+        const int oh0 = th * 8, ow0 = tw * 16;
+        const int ih0 = oh0 * s - a.pad, iw0 = ow0 * s - a.pad;
+        __syncthreads();
+        for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+            const int py = i / PW, px = i - py * PW;
+            int ih = ih0 + py, iw = iw0 + px;
+            if (a.pad_mode == 1) {
+                if (ih < 0) ih = -ih;
+                if (ih >= IH) ih = 2 * IH - 2 - ih;
+                if (iw < 0) iw = -iw;
+                if (iw >= IW) iw = 2 * IW - 2 - iw;
+            }
+            const bool ok = ih >= 0 && ih < IH && iw >= 0 && iw < IW;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (ok) {
+                const float* src = a.in + (((size_t)n * IH * R + (size_t)ih * R) * ((size_t)IW * R) + (size_t)iw * R) * CINP;
+                v0 = __ldg(reinterpret_cast<const float4*>(src));
+                if (CINP == 8) v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            }
+            *reinterpret_cast<float4*>(in_s + (size_t)i * CINP) = v0;
+            if (CINP == 8) *reinterpret_cast<float4*>(in_s + (size_t)i * CINP + 4) = v1;
+        }
+        __syncthreads();
+
+        float acc[8][CPT];
+#pragma unroll
+        for (int p_ = 0; p_ < 8; ++p_)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[p_][c] = 0.f;
+        for (int kh = 0; kh < KH; ++kh) {
+            const float* row = in_s + (size_t)((prow * s + kh) * PW) * CINP;
+            for (int kw = 0; kw < KW; ++kw) {
+                const float* wt = w_s + (size_t)((kh * KW + kw) * CINP) * Cout + c_base;
+#pragma unroll
+                for (int c4 = 0; c4 < CINP; c4 += 4) {
+                    float wv[4][CPT];
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                        for (int c = 0; c < CPT; c += 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(wt + (size_t)(c4 + ci) * Cout + c);
+                            wv[ci][c] = t.x; wv[ci][c + 1] = t.y; wv[ci][c + 2] = t.z; wv[ci][c + 3] = t.w;
+                        }
+#pragma unroll
+                    for (int p_ = 0; p_ < 8; ++p_) {
+                        const float4 iv = *reinterpret_cast<const float4*>(row + (size_t)((pcol0 + p_) * s + kw) * CINP + c4);
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            acc[p_][c] = fmaf(iv.x, wv[0][c], acc[p_][c]);
+                            acc[p_][c] = fmaf(iv.y, wv[1][c], acc[p_][c]);
+                            acc[p_][c] = fmaf(iv.z, wv[2][c], acc[p_][c]);
+                            acc[p_][c] = fmaf(iv.w, wv[3][c], acc[p_][c]);
+                        }
+                    }
+                }
+            }
+        }
+        const int oh = oh0 + prow;
+        if (oh < a.OH) {
+#pragma unroll
+            for (int p_ = 0; p_ < 8; ++p_) {
+                const int ow = ow0 + pcol0 + p_;
+                if (ow >= a.OW) continue;
+                const size_t pix = ((size_t)n * a.OH + oh) * a.OW + ow;
+                const float ps = a.pscale ? __ldg(a.pscale + pix) : 1.f;
+                const float pm = a.pmul ? __ldg(a.pmul + pix) : 1.f;
+                float y[CPT];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const float v = act_fn(acc[p_][c] * ps + bv[c], a.act) * pm;
+                    y[c] = a.round_out ? rtf32(v) : v;
+                }
+                if (a.out) {
+                    float* op = a.out + pix * Cout + c_base;
+#pragma unroll
+                    for (int c = 0; c < CPT; c += 4) *reinterpret_cast<float4*>(op + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+                }
+                if (a.out_hi) {
+                    uint16_t hi[CPT], lo[CPT];
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) split16(y[c], a.out16_fmt, hi[c], lo[c]);
+                    uint16_t* ohp = reinterpret_cast<uint16_t*>(a.out_hi) + pix * Cout + c_base;
+                    uint16_t* olp = a.out_lo ? reinterpret_cast<uint16_t*>(a.out_lo) + pix * Cout + c_base : nullptr;
+#pragma unroll
+                    for (int c = 0; c < CPT; c += 4) {
+                        *reinterpret_cast<uint2*>(ohp + c) = make_uint2(hi[c] | ((uint32_t)hi[c + 1] << 16), hi[c + 2] | ((uint32_t)hi[c + 3] << 16));
+                        if (olp) *reinterpret_cast<uint2*>(olp + c) = make_uint2(lo[c] | ((uint32_t)lo[c + 1] << 16), lo[c + 2] | ((uint32_t)lo[c + 3] << 16));
                     }
                 }
             }
@@ -805,6 +931,22 @@ extern "C" int mg_conv_thin(const mg_thin_args* a, void* stream) {
         if (e != cudaSuccess) return set_error((int)e, "thin attr: %s", cudaGetErrorString(e));              \
         thin_conv_kernel<CI, CP><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);          \
     } while (0)
+    static const int use_gemm = getenv("MG_THIN_GEMM") ? atoi(getenv("MG_THIN_GEMM")) : 1;
+    if (use_gemm && (a->Cout == 128 || a->Cout == 64)) {
+#define LAUNCH_TG(CI, CT)                                                                                     \
+    do {                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(thin_gemm_kernel<CI, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             200 * 1024);                                                     \
+        if (e != cudaSuccess) return set_error((int)e, "thin attr: %s", cudaGetErrorString(e));               \
+        int g1 = num_sms() * (CT == 8 ? 1 : 2); if (g1 > num_tiles) g1 = num_tiles;                                            \
+        thin_gemm_kernel<CI, CT><<<g1, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);             \
+    } while (0)
+        if (a->CinP == 4 && a->Cout == 128) LAUNCH_TG(4, 8);
+        else if (a->CinP == 4) LAUNCH_TG(4, 4);
+        else if (a->Cout == 128) LAUNCH_TG(8, 8);
+        else LAUNCH_TG(8, 4);
+        return check_launch("mg_conv_thin");
+    }
     if (a->CinP == 4 && cpl == 4) LAUNCH_THIN(4, 4);
     else if (a->CinP == 4) LAUNCH_THIN(4, 2);
     else if (cpl == 4) LAUNCH_THIN(8, 4);
@@ -1118,4 +1260,44 @@ extern "C" int mg_pack_weight_gb16(const float* wg, const float* wb, void* out, 
     if (BN % 64 != 0 || (2 * C) % BN != 0) return set_error(-2, "mg_pack_weight_gb16: bad BN %d for C %d", BN, C);
     pack_weight_gb16_kernel<<<ew_grid(2LL * C * I * KH * KW), 256, 0, ST(stream)>>>(wg, wb, (uint16_t*)out, C, I, KH, KW, BN, fmt, split);
     return check_launch("mg_pack_weight_gb16");
+}
+
+// ------------------------------------------------------------------------------------ channel padding to 32
+// out[n,i,j,0:32] = (c < CinP ? in[n, src_i, src_j, c] : 0) with optional nearest down-sampling by R (segmap) and
+// reflection padding by p (out is then [N,H+2p,W+2p,32]); values TF32-rounded: operand of the tcgen05 weight-gradient
+// kernel for the thin (3/4/7-channel input) convolutions.
+namespace mg {
+__global__ void pad_channels32_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int CinP, int R,
+                                      int p) {
+    const int OH = H + 2 * p, OW = W + 2 * p;
+    const long long total = (long long)N * OH * OW * 8;   // float4 groups of 32 channels
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = idx & 7;
+        long long t = idx >> 3;
+        const int j = t % OW; t /= OW;
+        const int i = t % OH;
+        const int n = t / OH;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g * 4 < CinP) {
+            int ih = i - p, iw = j - p;
+            if (ih < 0) ih = -ih;
+            if (ih >= H) ih = 2 * H - 2 - ih;
+            if (iw < 0) iw = -iw;
+            if (iw >= W) iw = 2 * W - 2 - iw;
+            v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)n * H * R + (size_t)ih * R) * ((size_t)W * R) + (size_t)iw * R) * CinP) + g);
+            v.x = rtf32(v.x); v.y = rtf32(v.y); v.z = rtf32(v.z); v.w = rtf32(v.w);
+        }
+        reinterpret_cast<float4*>(out)[idx] = v;
+    }
+}
+}  // namespace mg
+extern "C" int mg_pad_channels32(const float* in, float* out, int N, int H, int W, int CinP, int seg_resize, int reflect_pad,
+                                 void* stream) {
+    if (!in || !out) return set_error(-1, "mg_pad_channels32: null pointer");
+    if (CinP != 4 && CinP != 8) return set_error(-2, "mg_pad_channels32: CinP must be 4 or 8");
+    const int R = seg_resize > 0 ? seg_resize : 1;
+    pad_channels32_kernel<<<ew_grid((long long)N * (H + 2 * reflect_pad) * (W + 2 * reflect_pad) * 8), 256, 0, ST(stream)>>>(
+        in, out, N, H, W, CinP, R, reflect_pad);
+    return check_launch("mg_pad_channels32");
 }

@@ -97,7 +97,7 @@ def _spade_fwd(blk, name, src, shift, ns, nh, act, seg4, R, hw):
     return SimpleNamespace(sp=sp, src=src, shift=shift, ns=ns, nh=nh, act=act, g1=g1, h=h, wsh=wsh, R=R, hw=hw)
 
 
-def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4):
+def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     """Backward of conv(act(SPADE(src))) given dy; returns (dxhat, sums) for the BN backward of `src`."""
     _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad)
     w, isg, _ = _conv_weight(conv, inv_of)
@@ -119,7 +119,13 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4):
     del dgb
     da = ops.act_bwd(dactv, actv, _RELU)
     del dactv, actv
-    dwt = ops.thin_wgrad(seg4, da, 3, 3, 1, 1, seg_resize=S.R, in_hw=S.hw)
+    seg32 = seg_cache.get(S.R) if seg_cache is not None else None
+    if seg32 is None:
+        seg32 = ops.pad_channels32(seg4, seg_resize=S.R, in_hw=S.hw)
+        if seg_cache is not None:
+            seg_cache.clear()          # one resolution at a time is alive (blocks run coarse -> fine in reverse)
+            seg_cache[S.R] = seg32
+    dwt = ops.thin_wgrad_tc(seg32, da, 3, 3, 1, 1, 4)
     G.add(sp.mlp_shared[0].weight, _thin_wt_to_oihw(dwt, 3, 3, 4))
     G.add(sp.mlp_shared[0].bias, ops.chan_sum(da))
     return dxhat, allreduce_sums(sums)
@@ -149,6 +155,7 @@ def block_fwd(blk, x, xs, seg4, inv_of, blend):
 
 def block_bwd(G, blk, S, dout, seg4, inv_of):
     """-> (dx wrt the block input (pre-upsample), dbf wrt the blended background feature or None)."""
+    seg_cache = {}
     dbf = None
     if S.blend is not None:
         _, hair, back, ms = S.blend
@@ -157,15 +164,15 @@ def block_bwd(G, blk, S, dout, seg4, inv_of):
         dy = dout
     N = dy.shape[0]
     h, w = S.hw
-    dxhat1, sums1 = _spade_conv_bwd(G, blk, S.sp1, blk.conv_1, inv_of, dy, 3, 1, seg4)
+    dxhat1, sums1 = _spade_conv_bwd(G, blk, S.sp1, blk.conv_1, inv_of, dy, 3, 1, seg4, seg_cache)
     ddx = ops.bn_bwd_apply(dxhat1, S.dx, 0, S.sp1.ns, S.sp1.nh, sums1, N * h * w * _world())
     del dxhat1
-    dxhat0, sums0 = _spade_conv_bwd(G, blk, S.sp0, blk.conv_0, inv_of, ddx, 3, 1, seg4)
+    dxhat0, sums0 = _spade_conv_bwd(G, blk, S.sp0, blk.conv_0, inv_of, ddx, 3, 1, seg4, seg_cache)
     del ddx
     dx = ops.bn_bwd_apply(dxhat0, S.x, S.xs, S.sp0.ns, S.sp0.nh, sums0, S.count0)
     del dxhat0
     if blk.learned_shortcut:
-        dxhat_s, sums_s = _spade_conv_bwd(G, blk, S.sps, blk.conv_s, inv_of, dy, 1, 0, seg4)
+        dxhat_s, sums_s = _spade_conv_bwd(G, blk, S.sps, blk.conv_s, inv_of, dy, 1, 0, seg4, seg_cache)
         ops.bn_bwd_apply(dxhat_s, S.x, S.xs, S.sps.ns, S.sps.nh, sums_s, S.count0, dx=dx)
     else:
         ops.bn_bwd_apply(dy, S.x, S.xs, None, None, None, 1, dx=dx)   # identity shortcut through the upsample
@@ -212,7 +219,7 @@ def fc_bwd(G, fc, S, dout):
         dy = ops.in_bwd(da, L.y_in, L.ss, _LRELU, pmul=L.pm_in)
     dz = ops.act_bwd(dy, None, _NONE, pm1=S.l1.upd, pm2=S.l1.ratio)
     G.add(fc.layer1.bias, ops.chan_sum(ops.act_bwd(dy, None, _NONE, pm1=S.l1.upd)))
-    G.add(fc.layer1.weight, _thin_wt_to_oihw(ops.thin_wgrad(S.x0, dz, 3, 3, 2, 1), 3, 3, 3))
+    G.add(fc.layer1.weight, _thin_wt_to_oihw(ops.thin_wgrad_tc(ops.pad_channels32(S.x0), dz, 3, 3, 2, 1, 4), 3, 3, 3))
 
 
 def bg_fwd(bg, image, mask, noise):
@@ -248,7 +255,7 @@ def bg_bwd(G, bg, S, dfeats):
         d = ops.reflect_pad_bwd(dxp, 1, dx=d_list[i])
     dz0 = ops.act_bwd(d, S.x0, _RELU)
     G.add(bg.conv1.conv.bias, ops.chan_sum(dz0))
-    G.add(bg.conv1.conv.weight, _thin_wt_to_oihw(ops.thin_wgrad(S.inp, dz0, 7, 7, 1, 3, pad_mode=1), 7, 7, 3))
+    G.add(bg.conv1.conv.weight, _thin_wt_to_oihw(ops.thin_wgrad_tc(ops.pad_channels32(S.inp, reflect_pad=3), dz0, 7, 7, 1, 0, 4), 7, 7, 3))
 
 
 # =============================================================================================== generator Function
@@ -350,7 +357,7 @@ def _d_scale_bwd(G, D, S, douts, inv_of, need_dimg, param_grads):
     conv0 = D.model0[0]
     dz0 = ops.act_bwd(df, S.f0, _LRELU)
     if param_grads:
-        G.add(conv0.weight, _thin_wt_to_oihw(ops.thin_wgrad(S.x8, dz0, 4, 4, 2, D.padw), 4, 4, conv0.weight.shape[1]))
+        G.add(conv0.weight, _thin_wt_to_oihw(ops.thin_wgrad_tc(ops.pad_channels32(S.x8), dz0, 4, 4, 2, D.padw, 8), 4, 4, conv0.weight.shape[1]))
         G.add(conv0.bias, ops.chan_sum(dz0))
     if not need_dimg:
         return None

@@ -514,8 +514,27 @@ def in_bwd(df, x, ss, act=ACT_LRELU, pmul=None, round_tf32=False):
     return dx
 
 
+def pad_channels32(x, seg_resize=0, in_hw=None, reflect_pad=0):
+    """[N,H,W,CinP] -> TF32-rounded [N,H+2p,W+2p,32] (zero channel pad, optional nearest resize / reflect pad)."""
+    _chk(x, "x")
+    N = x.shape[0]
+    H, W = in_hw if seg_resize else (x.shape[1], x.shape[2])
+    out = torch.empty((N, H + 2 * reflect_pad, W + 2 * reflect_pad, 32), device=x.device, dtype=torch.float32)
+    check(_lib.load().mg_pad_channels32(_p(x), _p(out), N, H, W, x.shape[-1], seg_resize, reflect_pad, _stream()), "mg_pad_channels32")
+    return out
+
+
+def thin_wgrad_tc(x32, dz, kh, kw, stride, pad, cinp):
+    """Weight gradient of a thin conv on the tensor cores: x32 from pad_channels32 (already reflect-padded when the
+    conv uses reflection padding: pass pad=0 then).  Returns the thin layout [kh*kw][cinp][Cout]."""
+    cout = dz.shape[-1]
+    dwp = conv_wgrad(dz, x32, kh, kw, stride, pad)               # [Cout][kh*kw*32]
+    return dwp.view(cout, kh * kw, 32)[:, :, :cinp].permute(1, 2, 0).contiguous()
+
+
 def thin_wgrad(x, dz, kh, kw, stride, pad, pad_mode=0, seg_resize=0, in_hw=None):
-    """dwt [kh*kw][CinP][Cout] of a thin conv; x is the (possibly full-resolution seg) input."""
+    """dwt [kh*kw][CinP][Cout] of a thin conv; x is the (possibly full-resolution seg) input.
+    (CUDA-core reference kernel; the training path uses thin_wgrad_tc.)"""
     _chk(x, "x"); _chk(dz, "dz")
     N, OH, OW, Cout = dz.shape
     CinP = x.shape[-1]

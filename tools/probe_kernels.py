@@ -365,6 +365,11 @@ def group_bwd2():
         dw = dwt.view(k, k, CinP, Cout).permute(3, 2, 0, 1)[:, :Cin]
         torch.cuda.synchronize()
         report("thin_wgrad %d->%d k%d s%d pm%d" % (Cin, Cout, k, s_, pmode), dw, w.grad, 2e-5)
+        x32 = ops.pad_channels32(ops.nchw_to_nhwc(x.detach(), CinP), reflect_pad=p_ if pmode else 0)
+        dwt2 = ops.thin_wgrad_tc(x32, nhwc(dz), k, k, s_, 0 if pmode else p_, CinP)
+        dw2 = dwt2.view(k, k, CinP, Cout).permute(3, 2, 0, 1)[:, :Cin]
+        torch.cuda.synchronize()
+        report("thin_wgrad_tc %d->%d k%d s%d pm%d (tf32)" % (Cin, Cout, k, s_, pmode), dw2, w.grad, 2e-3)
         if Cin == 7:
             dimg = torch.zeros(2, 3, 32, 32, device=dev)
             ops.thin_dgrad3(nhwc(dz), ops.pack_weight_thin(w.detach(), 8), dimg, k, k, s_, p_, 4)
@@ -377,6 +382,8 @@ def group_bwd2():
     y.backward(dz)
     dwt = ops.thin_wgrad(nhwc(seg), nhwc(dz), 3, 3, 1, 1, seg_resize=4, in_hw=(16, 16))
     report("thin_wgrad seg_resize", dwt.view(3, 3, 4, 128).permute(3, 2, 0, 1), w.grad, 2e-5)
+    dwt2 = ops.thin_wgrad_tc(ops.pad_channels32(nhwc(seg), seg_resize=4, in_hw=(16, 16)), nhwc(dz), 3, 3, 1, 1, 4)
+    report("thin_wgrad_tc seg_resize (tf32)", dwt2.view(3, 3, 4, 128).permute(3, 2, 0, 1), w.grad, 2e-3)
     # ---- conv_img backward
     x = torch.randn(2, 64, 24, 40, generator=g).to(dev).requires_grad_(True)
     w = (torch.randn(3, 64, 3, 3, generator=g) / 24).to(dev).requires_grad_(True)
