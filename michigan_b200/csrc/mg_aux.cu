@@ -932,7 +932,8 @@ extern "C" int mg_conv_thin(const mg_thin_args* a, void* stream) {
         thin_conv_kernel<CI, CP><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);          \
     } while (0)
     static const int use_gemm = getenv("MG_THIN_GEMM") ? atoi(getenv("MG_THIN_GEMM")) : 1;
-    if (use_gemm && (a->Cout == 128 || a->Cout == 64)) {
+    // measured on B200: the register-tiled variant wins for Cout = 64 (k7 / k4 layers), the lane-per-channel one for Cout = 128
+    if ((use_gemm == 2 && a->Cout == 128) || (use_gemm >= 1 && a->Cout == 64)) {
 #define LAUNCH_TG(CI, CT)                                                                                     \
     do {                                                                                                      \
         cudaError_t e = cudaFuncSetAttribute(thin_gemm_kernel<CI, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
