@@ -62,6 +62,7 @@ struct IgemmParams {
     const float* bbias;
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
     int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default); scratch offset in smem
+    int dbg;   // what-if probes (env MG_DBG, results are WRONG): 1 no B loads after the first tile, 2 no A loads, 4 no epilogue work, 8 no epilogue global traffic
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -152,8 +153,9 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
-            const uint32_t tx = kABytes + p.BN * 128;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const bool ldA = !(p.dbg & 2) || tile == (int)blockIdx.x, ldB = !(p.dbg & 1) || tile == (int)blockIdx.x;
+                const uint32_t tx = (ldA ? kABytes : 0) + (ldB ? p.BN * 128 : 0);
                 const int nt = tile % p.n_tiles;
                 const int m = tile / p.n_tiles;
                 const int tw = m % p.tiles_w;
@@ -172,10 +174,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait(&empty_bar[st], ph ^ 1);
                             uint8_t* sa = smem + (size_t)st * stage_bytes;
-                            mbar_arrive_expect_tx(&full_bar[st], tx);
-                            tma_load_4d(sa, ta, &full_bar[st], kc * p.kelem, iw0 + kw, ih0 + kh, n0);
-                            tma_load_2d(sa + kABytes, &tmB, &full_bar[st], (tap * bparts + bsel) * p.Cin + kc * p.kelem,
-                                        nt * p.BN);
+                            if (tx == 0) { mbar_arrive(&full_bar[st]); }
+                            else mbar_arrive_expect_tx(&full_bar[st], tx);
+                            if (ldA) tma_load_4d(sa, ta, &full_bar[st], kc * p.kelem, iw0 + kw, ih0 + kh, n0);
+                            if (ldB) tma_load_2d(sa + kABytes, &tmB, &full_bar[st], (tap * bparts + bsel) * p.Cin + kc * p.kelem,
+                                                 nt * p.BN);
                             if (++st == p.stages) { st = 0; ph ^= 1; }
                         }
                     }
@@ -270,6 +273,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
             for (int cb = 0; cb < span; cb += cw) {
+                if (p.dbg & 4) break;
                 const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
                 float4 av[8], bv[8];
                 // TMEM chunk -> scratch (row per lane) -> registers (transposed: lanes cover contiguous channels)
@@ -309,7 +313,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const size_t pix = pixo[j];
                     float y[4];
                     if (spade) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)srco[j] * p.Cout + cch));
+                        const float4 xv = (p.dbg & 8) ? sc4 : __ldg(reinterpret_cast<const float4*>(p.x + (size_t)srco[j] * p.Cout + cch));
                         const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
                         if (has_aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + cch) = gs;
                         y[0] = fmaf(fmaf(xv.x, sc4.x, sh4.x), gs.x, bb4.x + bv[j].x);
@@ -353,7 +357,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         *op = make_float4(y[0], y[1], y[2], y[3]);
                     }
-                    if (has_hi) {
+                    if (has_hi && !((p.dbg & 8) && y[0] != 12345.f)) {
                         uint32_t hi[2], lo[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -602,6 +606,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     int stages = (227 * 1024 - 1024 - 512 - scratch_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     static const int stages_cap = getenv("MG_STAGES") ? atoi(getenv("MG_STAGES")) : 0;
+    p.dbg = getenv("MG_DBG") ? atoi(getenv("MG_DBG")) : 0;
     if (stages_cap > 0 && stages > stages_cap) stages = stages_cap;
     p.stages = stages;
     p.epi_off = stages * stage_bytes + 512;

@@ -19,14 +19,13 @@
 namespace mg {
 
 constexpr int kWgThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int kPixTile = 64;          // K per pipeline stage
-constexpr int kBoxBytes = kPixTile * 128;  // one [64 px x 32 ch] fp32 box
 constexpr int kWgStagesMax = 6;
 
 struct WgradParams {
     int N, OH, OW, Cout, Cin, KH, KW, stride, pad;
     int TW, TH, TN, tiles_w, tiles_h, tiles_n, pix_tiles;
     int BN, m_tiles, n_tiles, splits, stages;
+    int pix_tile, box_bytes;   // K (pixels) per pipeline stage: 32 or 64; bytes of one [pix_tile x 32 ch] box
     uint32_t idesc, tmem_cols;
     float* dw;  // [Cout][KH*KW*Cin]
 };
@@ -49,9 +48,12 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // One unit = one filter ROW (kh): the dY tile is loaded once per stage and multiplied with the KW shifted
+    // input tiles (accumulators kw*BN.. in TMEM), so dY is streamed KH (not KH*KW) times from HBM/L2.
+    const int kBoxBytes = p.box_bytes;
     const int a_bytes = 4 * kBoxBytes;                 // M = 128 -> 4 boxes
-    const int b_bytes = (p.BN / 32) * kBoxBytes;
-    const int stage_bytes = a_bytes + b_bytes;
+    const int b1_bytes = (p.BN / 32) * kBoxBytes;      // one tap's input tile
+    const int stage_bytes = a_bytes + p.KW * b1_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgStagesMax;
@@ -59,13 +61,12 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStagesMax + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // unit decode: blockIdx.x = ((tap * m_tiles + mt) * n_tiles + nt) * splits + split
+    // unit decode: blockIdx.x = ((kh * m_tiles + mt) * n_tiles + nt) * splits + split
     int u = blockIdx.x;
     const int split = u % p.splits; u /= p.splits;
     const int nt = u % p.n_tiles; u /= p.n_tiles;
     const int mt = u % p.m_tiles;
-    const int tap = u / p.m_tiles;
-    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+    const int kh = u / p.m_tiles;
     const int t_begin = (int)((long long)p.pix_tiles * split / p.splits);
     const int t_end = (int)((long long)p.pix_tiles * (split + 1) / p.splits);
 
@@ -96,9 +97,10 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                 mbar_arrive_expect_tx(&full_bar[st], tx);
                 for (int j = 0; j < 4; ++j)
                     tma_load_4d(sa + j * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + j * 32, ow0, oh0, n0);
-                for (int j = 0; j < p.BN / 32; ++j)
-                    tma_load_4d(sa + a_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * 32,
-                                ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
+                for (int kw = 0; kw < p.KW; ++kw)
+                    for (int j = 0; j < p.BN / 32; ++j)
+                        tma_load_4d(sa + a_bytes + kw * b1_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * 32,
+                                    ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }
         }
@@ -110,13 +112,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-#pragma unroll
-                for (int k = 0; k < kPixTile / 8; ++k) {
-                    const uint64_t da = umma_desc_mnmajor_sw128(sa + k * 1024, kBoxBytes);
-                    const uint64_t db = umma_desc_mnmajor_sw128(sa + a_bytes + k * 1024, kBoxBytes);
-                    umma_tf32(tmem_base, da, db, p.idesc, first ? 0u : 1u);
-                    first = 0;
-                }
+                for (int kw = 0; kw < p.KW; ++kw)
+                    for (int k = 0; k < p.pix_tile / 8; ++k) {
+                        const uint64_t da = umma_desc_mnmajor_sw128(sa + k * 1024, kBoxBytes);
+                        const uint64_t db = umma_desc_mnmajor_sw128(sa + a_bytes + kw * b1_bytes + k * 1024, kBoxBytes);
+                        umma_tf32(tmem_base + (uint32_t)(kw * p.BN), da, db, p.idesc, (first && k == 0) ? 0u : 1u);
+                    }
+                first = 0;
                 umma_commit(&empty_bar[st]);
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }
@@ -130,18 +132,20 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             mbar_wait(done_bar, 0);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-            float* dst = p.dw + (size_t)co * (p.KH * p.KW * p.Cin) + (size_t)tap * p.Cin + nt * p.BN;
-            for (int j0 = 0; j0 < p.BN; j0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_row + j0, v);
-                tmem_ld_wait();
-                if (co < p.Cout) {
+            for (int kw = 0; kw < p.KW; ++kw) {
+                float* dst = p.dw + (size_t)co * (p.KH * p.KW * p.Cin) + (size_t)(kh * p.KW + kw) * p.Cin + nt * p.BN;
+                for (int j0 = 0; j0 < p.BN; j0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + kw * p.BN + j0, v);
+                    tmem_ld_wait();
+                    if (co < p.Cout) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float4 val = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                                 __uint_as_float(v[i + 3]));
-                        if (p.splits > 1) atomicAdd(reinterpret_cast<float4*>(dst + j0 + i), val);
-                        else *reinterpret_cast<float4*>(dst + j0 + i) = val;
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 val = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                                     __uint_as_float(v[i + 3]));
+                            if (p.splits > 1) atomicAdd(reinterpret_cast<float4*>(dst + j0 + i), val);
+                            else *reinterpret_cast<float4*>(dst + j0 + i) = val;
+                        }
                     }
                 }
             }
@@ -167,29 +171,36 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
     WgradParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout; p.Cin = Cin; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
-    p.TW = np2(OW) < 8 ? np2(OW) : 8;
-    int th = kPixTile / p.TW;
-    p.TH = np2(OH) < th ? np2(OH) : th;
-    p.TN = kPixTile / (p.TW * p.TH);
-    p.tiles_w = (OW + p.TW - 1) / p.TW; p.tiles_h = (OH + p.TH - 1) / p.TH; p.tiles_n = (N + p.TN - 1) / p.TN;
-    p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     int BN = Cin >= 128 ? 128 : Cin;
     if (Cin % BN != 0) BN = 32;
+    while (KW * BN > 512) BN /= 2;                       // KW accumulators of BN columns must fit TMEM
+    if (BN < 32 || Cin % BN != 0) return set_error(-3, "mg_conv_wgrad: KW %d x Cin %d does not fit TMEM", KW, Cin);
     p.BN = BN;
+    // K (pixels) per stage: 64 when at least 3 stages fit in shared memory, else 32
+    int pix_tile = 64;
+    if ((200 * 1024) / ((4 + KW * (BN / 32)) * 64 * 128) < 3) pix_tile = 32;
+    p.pix_tile = pix_tile; p.box_bytes = pix_tile * 128;
+    p.TW = np2(OW) < 8 ? np2(OW) : 8;
+    int th = pix_tile / p.TW;
+    p.TH = np2(OH) < th ? np2(OH) : th;
+    p.TN = pix_tile / (p.TW * p.TH);
+    p.tiles_w = (OW + p.TW - 1) / p.TW; p.tiles_h = (OH + p.TH - 1) / p.TH; p.tiles_n = (N + p.TN - 1) / p.TN;
+    p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.m_tiles = (Cout + 127) / 128;
     p.n_tiles = Cin / BN;
-    const int units = KH * KW * p.m_tiles * p.n_tiles;
+    const int units = KH * p.m_tiles * p.n_tiles;
     int splits = (2 * num_sms() + units - 1) / units;
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     if (splits < 1) splits = 1;
     p.splits = splits;
-    const int stage_bytes = 4 * kBoxBytes + (BN / 32) * kBoxBytes;
+    const int stage_bytes = (4 + KW * (BN / 32)) * p.box_bytes;
     int stages = (200 * 1024) / stage_bytes;
+    if (stages < 1) return set_error(-4, "mg_conv_wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
     if (stages > kWgStagesMax) stages = kWgStagesMax;
     p.stages = stages;
     // TF32 x TF32 -> F32, A and B both MN-major (bits 15, 16), M = 128, N = BN
     p.idesc = umma_idesc_tf32(128, BN) | (1u << 15) | (1u << 16);
-    int tc = np2(BN); p.tmem_cols = tc < 32 ? 32 : tc;
+    int tc = np2(KW * BN); p.tmem_cols = tc < 32 ? 32 : tc;
     p.dw = dw;
 
     CUtensorMap tmDY, tmX;
