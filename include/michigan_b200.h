@@ -27,6 +27,8 @@ int mg_version(void);
 const char* mg_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 long long mg_launch_count(void);
+/* debugging aid: 16 clock64() totals CTA 0 of mg_conv_igemm recorded under env MG_DBG=16 (producer / MMA / epilogue waits) */
+int mg_debug_igemm_prof(unsigned long long* host16);
 
 /* activation codes */
 #define MG_ACT_NONE 0

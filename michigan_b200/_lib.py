@@ -56,6 +56,7 @@ SIGNATURES = {
     "mg_version": [],
     "mg_last_error": [],
     "mg_launch_count": [],
+    "mg_debug_igemm_prof": [C.c_void_p],
     "mg_conv_igemm": [C.POINTER(IgemmArgs), _p],
     "mg_pack_weight": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
     "mg_pack_weight_gb": [_p, _p, _p, _i, _i, _i, _i, _i, _p],

@@ -31,6 +31,10 @@ constexpr int kNumEpiWarps = 8;
 constexpr int kThreads = 64 + kNumEpiWarps * 32;  // 320
 constexpr int kABytes = 128 * 128;                // 128 pixels x 32 fp32
 constexpr int kMaxStages = 8;
+constexpr int kMaxASlots = 4;
+
+// MG_DBG & 16: CTA 0 records clock64() totals here (see mg_debug_igemm_prof)
+__device__ unsigned long long g_igemm_prof[16];
 
 struct IgemmParams {
     int N, OH, OW, Cout;
@@ -62,7 +66,10 @@ struct IgemmParams {
     const float* bbias;
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
     int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default); scratch offset in smem
-    int dbg;   // what-if probes (env MG_DBG, results are WRONG): 1 no B loads after the first tile, 2 no A loads, 4 no epilogue work, 8 no epilogue global traffic
+    // halo mode (3x3, stride 1, pad 1): one [PW x (TH+2)] input patch per K chunk serves all 9 taps
+    int halo, PW, patch_bytes, patch_tx, a_slots, b_slots, b_slot_bytes, acc_cols, merged, n_items, bo_mode, bar_off;
+    uint32_t idesc2;
+    int dbg;   // what-if probes (env MG_DBG; 1..8 give WRONG results): 1 no B loads after the first tile, 2 no A loads, 4 no epilogue work, 8 no epilogue global traffic (32 no 16-bit stores only, 64 no x loads only), 16 cycle profile
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -112,12 +119,14 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 1024-align the operand ring (SWIZZLE_128B atoms are 1024 B).
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = kABytes + p.BN * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t* full_bar = bars;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+    uint64_t* full_bar = bars;                        // halo mode: the weight (B) ring
     uint64_t* empty_bar = bars + kMaxStages;
     uint64_t* tfull_bar = bars + 2 * kMaxStages;
     uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    uint64_t* afull_bar = bars + 2 * kMaxStages + 5;  // halo mode: the patch (A) ring, <= kMaxASlots slots
+    uint64_t* aempty_bar = afull_bar + kMaxASlots;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,9 +135,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < p.stages; ++s) {
+        for (int s = 0; s < (p.halo ? p.b_slots : p.stages); ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < p.a_slots; ++s) {
+            mbar_init(&afull_bar[s], 1);
+            mbar_init(&aempty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -148,11 +161,121 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ksteps = p.KH * p.KW * p.parts * p.kchunks;
     const int m_tiles_per_img = p.tiles_w * p.tiles_h;
 
-    if (warp == 0) {
+    if (warp == 0 && p.halo) {
+        // ===================== TMA producer, halo mode (one thread) =====================
+        // Two rings: A = input patches (one per K chunk [x hi/lo part], reused by all 9 taps), B = weights
+        // (one slot per tap).  A patches are prefetched up to a_slots-1 items ahead of the weight stream.
+        if (lane == 0) {
+            const int parts2 = p.merged ? 2 : 1;
+            const int bparts = p.merged ? 2 : 1;
+            uint8_t* a_ring = smem;
+            uint8_t* b_ring = smem + (size_t)p.a_slots * p.patch_bytes;
+            int bs = 0, as_ = 0;
+            uint32_t bph = 0, aphs = 0;
+            long long a_issued = 0, b_item = 0;
+            int tileA = blockIdx.x, itA = 0;
+            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            long long w_empty = 0, t_begin = prof ? clock64() : 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                for (int it = 0; it < p.n_items; ++it, ++b_item) {
+                    const int kc = it / parts2, part = it - kc * parts2;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        while (tileA < p.num_tiles && a_issued < b_item + p.a_slots) {
+                            const bool must = a_issued <= b_item;
+                            if (!must && !mbar_test_wait(&aempty_bar[as_], aphs ^ 1)) break;
+                            if (must) mbar_wait(&aempty_bar[as_], aphs ^ 1);
+                            const int mA = tileA / p.n_tiles;
+                            const int twA = mA % p.tiles_w, thA = (mA / p.tiles_w) % p.tiles_h, tnA = mA / m_tiles_per_img;
+                            const int kcA = itA / parts2, partA = itA - kcA * parts2;
+                            mbar_arrive_expect_tx(&afull_bar[as_], (uint32_t)p.patch_tx);
+                            tma_load_4d(a_ring + (size_t)as_ * p.patch_bytes, partA ? &tmA2 : &tmA, &afull_bar[as_], kcA * p.kelem,
+                                        twA * p.TW - 1, thA * p.TH - 1, tnA);
+                            if (++as_ == p.a_slots) { as_ = 0; aphs ^= 1; }
+                            if (++itA == p.n_items) { itA = 0; tileA += gridDim.x; }
+                            ++a_issued;
+                        }
+                        const long long t0 = prof ? clock64() : 0;
+                        mbar_wait(&empty_bar[bs], bph ^ 1);
+                        if (prof) w_empty += clock64() - t0;
+                        uint8_t* sb = b_ring + (size_t)bs * p.b_slot_bytes;
+                        const int kofs = tap * bparts * p.Cin + kc * p.kelem;
+                        if (p.merged && part == 0) {
+                            // A_hi x [W_hi ; W_lo]: both weight parts side by side -> one N = 2*BN MMA
+                            mbar_arrive_expect_tx(&full_bar[bs], (uint32_t)(2 * p.BN * 128));
+                            tma_load_2d(sb, &tmB, &full_bar[bs], kofs, nt * p.BN);
+                            tma_load_2d(sb + p.BN * 128, &tmB, &full_bar[bs], kofs + p.Cin, nt * p.BN);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[bs], (uint32_t)(p.BN * 128));
+                            tma_load_2d(sb, &tmB, &full_bar[bs], kofs, nt * p.BN);
+                        }
+                        if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+                    }
+                }
+            }
+            if (prof) { g_igemm_prof[0] = (unsigned long long)(clock64() - t_begin); g_igemm_prof[1] = (unsigned long long)w_empty; }
+        }
+    } else if (warp == 1 && p.halo) {
+        // ===================== MMA issuer, halo mode (one thread) =====================
+        if (lane == 0) {
+            const int parts2 = p.merged ? 2 : 1;
+            const uint32_t a_ring = smem_u32(smem);
+            const uint32_t b_ring = a_ring + (uint32_t)(p.a_slots * p.patch_bytes);
+            int bs = 0, as_ = 0, acc = 0;
+            uint32_t bph = 0, aphs = 0, aph = 0;
+            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            long long w_tempty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                long long t0 = prof ? clock64() : 0;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                if (prof) w_tempty += clock64() - t0;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+                for (int it = 0; it < p.n_items; ++it) {
+                    const int part = it % parts2;
+                    const uint32_t idesc = (p.merged && part == 1) ? p.idesc2 : p.idesc;
+                    t0 = prof ? clock64() : 0;
+                    mbar_wait(&afull_bar[as_], aphs);
+                    if (prof) w_full += clock64() - t0;
+                    const uint32_t a_base = a_ring + (uint32_t)(as_ * p.patch_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        t0 = prof ? clock64() : 0;
+                        mbar_wait(&full_bar[bs], bph);
+                        if (prof) w_full += clock64() - t0;
+                        tc_fence_after();
+                        // tap (kh, kw) = the same patch read from row kh*PW + kw on; 8-pixel row groups are PW rows apart
+                        const uint32_t a_tap = a_base + (uint32_t)((kh * p.PW + kw) * 128);
+                        const uint64_t db = umma_desc_kmajor_sw128(b_ring + (uint32_t)(bs * p.b_slot_bytes));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t a_addr = a_tap + (uint32_t)(k * 32);
+                            const uint64_t da = umma_desc_sw128_general(a_addr, (uint32_t)(p.PW * 128), p.bo_mode ? (a_addr >> 7) & 7u : 0u);
+                            const uint32_t accum = (it | tap | k) != 0 ? 1u : 0u;
+                            if (p.a_fmt == 0) umma_tf32(d_tmem, da, db + (uint64_t)(2 * k), idesc, accum);
+                            else umma_f16(d_tmem, da, db + (uint64_t)(2 * k), idesc, accum);
+                        }
+                        umma_commit(&empty_bar[bs]);
+                        if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+                    }
+                    umma_commit(&aempty_bar[as_]);
+                    if (++as_ == p.a_slots) { as_ = 0; aphs ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; aph ^= 1; }
+            }
+            if (prof) {
+                g_igemm_prof[2] = (unsigned long long)(clock64() - t_begin);
+                g_igemm_prof[3] = (unsigned long long)w_tempty; g_igemm_prof[4] = (unsigned long long)w_full;
+            }
+        }
+    } else if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
+            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            long long w_empty = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const bool ldA = !(p.dbg & 2) || tile == (int)blockIdx.x, ldB = !(p.dbg & 1) || tile == (int)blockIdx.x;
                 const uint32_t tx = (ldA ? kABytes : 0) + (ldB ? p.BN * 128 : 0);
@@ -172,7 +295,9 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const CUtensorMap* ta = part == 1 ? &tmA2 : &tmA;
                         const int bsel = part == 2 ? 1 : 0;
                         for (int kc = 0; kc < p.kchunks; ++kc) {
+                            const long long t0 = prof ? clock64() : 0;
                             mbar_wait(&empty_bar[st], ph ^ 1);
+                            if (prof) w_empty += clock64() - t0;
                             uint8_t* sa = smem + (size_t)st * stage_bytes;
                             if (tx == 0) { mbar_arrive(&full_bar[st]); }
                             else mbar_arrive_expect_tx(&full_bar[st], tx);
@@ -184,6 +309,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
             }
+            if (prof) { g_igemm_prof[0] = (unsigned long long)(clock64() - t_begin); g_igemm_prof[1] = (unsigned long long)w_empty; }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
@@ -192,12 +318,18 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t ph = 0;
             int acc = 0;
             uint32_t aph = 0;
+            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            long long w_tempty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                long long t0 = prof ? clock64() : 0;
                 mbar_wait(&tempty_bar[acc], aph ^ 1);
+                if (prof) w_tempty += clock64() - t0;
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 for (int ks = 0; ks < ksteps; ++ks) {
+                    t0 = prof ? clock64() : 0;
                     mbar_wait(&full_bar[st], ph);
+                    if (prof) w_full += clock64() - t0;
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
@@ -215,6 +347,10 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; aph ^= 1; }
+            }
+            if (prof) {
+                g_igemm_prof[2] = (unsigned long long)(clock64() - t_begin);
+                g_igemm_prof[3] = (unsigned long long)w_tempty; g_igemm_prof[4] = (unsigned long long)w_full;
             }
         }
     } else if (p.epi_impl == 1) {
@@ -245,6 +381,9 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ch_tile = p.BN >> 1;
         int acc = 0;
         uint32_t aph = 0;
+        const bool prof = (p.dbg & 16) && blockIdx.x == 0 && (ew == 0 || ew == 7) && lane == 0;
+        long long w_tfull = 0, busy = 0, t_begin = prof ? clock64() : 0;
+        int ntile = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int m = tile / p.n_tiles;
@@ -252,11 +391,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int th = (m / p.tiles_w) % p.tiles_h;
             const int tn = m / m_tiles_per_img;
             // per-tile pixel bookkeeping for the (up to 8) pixels this lane serves in the transposed domain
-            uint32_t pixo[8], srco[8], msko[8];
+            uint32_t pixo[8], srco[8];
             uint32_t vmask = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                pixo[j] = srco[j] = msko[j] = 0;
+                pixo[j] = srco[j] = 0;
                 if (j >= passes) continue;
                 const int r = quarter * 32 + j * ppp + psub;
                 const int ow = tw * p.TW + (r & (p.TW - 1));
@@ -267,17 +406,27 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 pixo[j] = (uint32_t)(((size_t)n * p.OHF + (size_t)oh * p.os + p.ooh) * p.OWF + (size_t)ow * p.os + p.oow);
                 if (spade) srco[j] = (uint32_t)(((size_t)n * p.XH + (oh >> p.x_shift)) * p.XW + (ow >> p.x_shift));
                 else if (p.res) srco[j] = (uint32_t)(((size_t)n * p.RH + (oh >> p.res_shift)) * p.RW + (ow >> p.res_shift));
-                if (p.bf) msko[j] = (uint32_t)(((size_t)n * p.MH + (size_t)oh * p.mask_stride) * p.MW + (size_t)ow * p.mask_stride);
             }
+            long long t0 = prof ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], aph);
+            if (prof) { const long long t1 = clock64(); w_tfull += t1 - t0; t0 = t1; }
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             for (int cb = 0; cb < span; cb += cw) {
                 if (p.dbg & 4) break;
                 const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
-                float4 av[8], bv[8];
+                float4 av[8], bv[8], pre[8];
+                const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
+                // Issue the per-pixel side loads (SPADE: the tensor being normalised; else the residual) FIRST so that
+                // their L2 latency overlaps the TMEM -> scratch -> register transposition below.
+                const float* side = spade ? p.x : p.res;
+                if (side != nullptr && cch < p.Cout && !(p.dbg & (8 | 64))) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((vmask >> j) & 1u) pre[j] = __ldg(reinterpret_cast<const float4*>(side + (size_t)srco[j] * p.Cout + cch));
+                }
                 // TMEM chunk -> scratch (row per lane) -> registers (transposed: lanes cover contiguous channels)
-                auto load_chunk = [&](int colbase, float4 (&dst)[8]) {
+                auto load_chunk = [&](int colbase, float4 (&dst)[8], bool add) {
                     for (int s0 = 0; s0 < cw; s0 += 16) {
                         uint32_t v[16];
                         tmem_ld16(t_row + (uint32_t)(colbase + s0), v);
@@ -291,35 +440,51 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (j < passes) dst[j] = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
+                        if (j < passes) {
+                            const float4 t = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
+                            if (add) { dst[j].x += t.x; dst[j].y += t.y; dst[j].z += t.z; dst[j].w += t.w; }
+                            else dst[j] = t;
+                        }
                     __syncwarp();
                 };
-                load_chunk(col, av);
-                if (spade) load_chunk(col + ch_tile, bv);
-                const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
-                if (cch >= p.Cout) continue;
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = bias4, sh4 = bias4, g14 = bias4, bb4 = bias4;
-                if (spade) {
-                    sc4 = __ldg(reinterpret_cast<const float4*>(p.nscale + cch));
-                    sh4 = __ldg(reinterpret_cast<const float4*>(p.nshift + cch));
-                    g14 = __ldg(reinterpret_cast<const float4*>(p.gbias1 + cch));
-                    bb4 = __ldg(reinterpret_cast<const float4*>(p.bbias + cch));
-                } else if (p.bias) {
-                    bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + cch));
+                const bool ch_ok = cch < p.Cout;
+                if (ch_ok) {
+                    if (spade) {
+                        sc4 = __ldg(reinterpret_cast<const float4*>(p.nscale + cch));
+                        sh4 = __ldg(reinterpret_cast<const float4*>(p.nshift + cch));
+                        g14 = __ldg(reinterpret_cast<const float4*>(p.gbias1 + cch));
+                        bb4 = __ldg(reinterpret_cast<const float4*>(p.bbias + cch));
+                    } else if (p.bias) {
+                        bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + cch));
+                    }
                 }
+                load_chunk(col, av, false);
+                if (p.merged) load_chunk(col + p.BN, av, true);   // split precision, merged N: + A_hi * W_lo columns
+                if (spade) {
+                    // fold gamma into the normalised input right away (frees `pre` before beta is fetched):
+                    // av <- (x * rstd + shift) * (1 + gamma)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!((vmask >> j) & 1u) || !ch_ok) continue;
+                        const float4 xv = (p.dbg & (8 | 64)) ? sc4 : pre[j];
+                        const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
+                        if (has_aux) *reinterpret_cast<float4*>(p.aux + (size_t)pixo[j] * p.Cout + cch) = gs;
+                        av[j] = make_float4(fmaf(xv.x, sc4.x, sh4.x) * gs.x, fmaf(xv.y, sc4.y, sh4.y) * gs.y,
+                                            fmaf(xv.z, sc4.z, sh4.z) * gs.z, fmaf(xv.w, sc4.w, sh4.w) * gs.w);
+                    }
+                    load_chunk(col + ch_tile, bv, false);
+                    if (p.merged) load_chunk(col + ch_tile + p.BN, bv, true);
+                }
+                if (!ch_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (!((vmask >> j) & 1u)) continue;
                     const size_t pix = pixo[j];
                     float y[4];
                     if (spade) {
-                        const float4 xv = (p.dbg & 8) ? sc4 : __ldg(reinterpret_cast<const float4*>(p.x + (size_t)srco[j] * p.Cout + cch));
-                        const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
-                        if (has_aux) *reinterpret_cast<float4*>(p.aux + pix * p.Cout + cch) = gs;
-                        y[0] = fmaf(fmaf(xv.x, sc4.x, sh4.x), gs.x, bb4.x + bv[j].x);
-                        y[1] = fmaf(fmaf(xv.y, sc4.y, sh4.y), gs.y, bb4.y + bv[j].y);
-                        y[2] = fmaf(fmaf(xv.z, sc4.z, sh4.z), gs.z, bb4.z + bv[j].z);
-                        y[3] = fmaf(fmaf(xv.w, sc4.w, sh4.w), gs.w, bb4.w + bv[j].w);
+                        y[0] = av[j].x + (bb4.x + bv[j].x); y[1] = av[j].y + (bb4.y + bv[j].y);
+                        y[2] = av[j].z + (bb4.z + bv[j].z); y[3] = av[j].w + (bb4.w + bv[j].w);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], act);
                     } else {
@@ -327,13 +492,17 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         y[0] = fmaf(av[j].x, ps, bias4.x); y[1] = fmaf(av[j].y, ps, bias4.y);
                         y[2] = fmaf(av[j].z, ps, bias4.z); y[3] = fmaf(av[j].w, ps, bias4.w);
                         if (p.res) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)srco[j] * p.Cout + cch));
+                            const float4 rv = pre[j];
                             y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], act);
                         if (p.bf) {
-                            const size_t mp = msko[j];
+                            // full-resolution mask coordinates of this output pixel (blend epilogue only)
+                            const int rr = quarter * 32 + j * ppp + psub;
+                            const size_t mp = ((size_t)(tn * p.TN + (rr >> (twl + thl))) * p.MH +
+                                               (size_t)(th * p.TH + ((rr >> twl) & (p.TH - 1))) * p.mask_stride) * p.MW +
+                                              (size_t)(tw * p.TW + (rr & (p.TW - 1))) * p.mask_stride;
                             const float om_hair = 1.f - __ldg(p.hair + mp), om_back = 1.f - __ldg(p.back + mp);
                             const float4 bfv = __ldg(reinterpret_cast<const float4*>(p.bf + pix * p.Cout + cch));
                             y[0] = bfv.x * om_hair + y[0] * om_back; y[1] = bfv.y * om_hair + y[1] * om_back;
@@ -357,7 +526,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         *op = make_float4(y[0], y[1], y[2], y[3]);
                     }
-                    if (has_hi && !((p.dbg & 8) && y[0] != 12345.f)) {
+                    if (has_hi && !((p.dbg & (8 | 32)) && y[0] != 12345.f)) {
                         uint32_t hi[2], lo[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -384,7 +553,13 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
+            if (prof) { busy += clock64() - t0; ++ntile; }
             if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+        if (prof) {
+            const int o = ew == 0 ? 5 : 9;
+            g_igemm_prof[o] = (unsigned long long)(clock64() - t_begin); g_igemm_prof[o + 1] = (unsigned long long)w_tfull;
+            g_igemm_prof[o + 2] = (unsigned long long)busy; g_igemm_prof[o + 3] = (unsigned long long)ntile;
         }
     } else {
         // ===================== epilogue warps (row-per-lane reference implementation) =====================
@@ -583,10 +758,37 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.OHF = a->OHF > 0 ? a->OHF : a->OH; p.OWF = a->OWF > 0 ? a->OWF : a->OW; p.accumulate = a->accumulate;
     if (p.os != 1 && (a->epi != MG_EPI_BIAS || a->res || a->bf || a->pscale || a->pmul))
         return set_error(-8, "mg_conv_igemm: strided output supports the plain bias epilogue only");
-    p.TW = next_pow2(a->OW) < 16 ? next_pow2(a->OW) : 16;
-    int th = 128 / p.TW;
-    p.TH = next_pow2(a->OH) < th ? next_pow2(a->OH) : th;
-    p.TN = 128 / (p.TW * p.TH);
+    static const int epi_impl_bias = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
+    static const int epi_impl_spade = getenv("MG_EPI_IMPL_SPADE") ? atoi(getenv("MG_EPI_IMPL_SPADE")) : epi_impl_bias;
+    const int epi_impl_env = a->epi == MG_EPI_SPADE ? epi_impl_spade : epi_impl_bias;
+    static const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 0;
+    p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
+    const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * 36 * 4 : 0;
+    // Halo mode: 3x3 / stride 1 / pad 1 convolutions (the SPADE gamma|beta GEMMs, conv_0/conv_1 and their dgrads) load
+    // one [PW x (TH+2)] input patch per K chunk and read the 9 taps out of it through shifted UMMA descriptors.
+    // MG_HALO: 0 off (default: measured no faster on B200 - these kernels are bound by the MMA operand fetch / epilogue,
+    // not by L2->smem traffic, see profiles/r01_prof_conv_*.log), 1 on; MG_HALO_PW: patch pitch in pixels (10 = exact, 16 = swizzle-atom aligned rows);
+    // MG_HALO_BO: 1 = set the descriptor's matrix-base-offset field from the start address (measured on B200: WRONG results;
+    // the hardware applies the 128B swizzle on absolute shared-memory address bits, so the field must stay 0).
+    const int halo_env = getenv("MG_HALO") ? atoi(getenv("MG_HALO")) : 0;
+    const int halo_pw = getenv("MG_HALO_PW") ? atoi(getenv("MG_HALO_PW")) : 10;
+    p.bo_mode = getenv("MG_HALO_BO") ? atoi(getenv("MG_HALO_BO")) : 0;
+    bool halo = halo_env && p.epi_impl == 1 && a->KH == 3 && a->KW == 3 && a->stride == 1 && p.pad_h == 1 && p.pad_w == 1 &&
+                a->OH >= 16 && a->OW >= 8 && a->H == a->OH && a->W == a->OW && (halo_pw == 10 || halo_pw == 16);
+    if (halo && a->split) {
+        // merged split precision: A_hi x [W_hi ; W_lo] (N = 2*BN) + A_lo x W_hi (N = BN); accumulator = 2*BN columns
+        if (a->BN == 0 && BN > 128) BN = 128;
+        if (BN > 128 || coutg % BN != 0) halo = false;
+    }
+    p.halo = halo ? 1 : 0;
+    p.merged = (halo && a->split) ? 1 : 0;
+    if (halo) { p.TW = 8; p.TH = 16; p.TN = 1; }
+    else {
+        p.TW = next_pow2(a->OW) < 16 ? next_pow2(a->OW) : 16;
+        int th = 128 / p.TW;
+        p.TH = next_pow2(a->OH) < th ? next_pow2(a->OH) : th;
+        p.TN = 128 / (p.TW * p.TH);
+    }
     p.tiles_w = (a->OW + p.TW - 1) / p.TW;
     p.tiles_h = (a->OH + p.TH - 1) / p.TH;
     p.tiles_n = (a->N + p.TN - 1) / p.TN;
@@ -596,22 +798,40 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.kchunks = a->Cin / kelem;
     p.a_fmt = a->a_fmt; p.parts = a->split ? 3 : 1; p.kelem = kelem;
     p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
-    const int stage_bytes = kABytes + BN * 128;
-    static const int epi_impl_bias = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
-    static const int epi_impl_spade = getenv("MG_EPI_IMPL_SPADE") ? atoi(getenv("MG_EPI_IMPL_SPADE")) : epi_impl_bias;
-    const int epi_impl_env = a->epi == MG_EPI_SPADE ? epi_impl_spade : epi_impl_bias;
-    static const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 0;
-    p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
-    const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * 36 * 4 : 0;
-    int stages = (227 * 1024 - 1024 - 512 - scratch_bytes) / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    static const int stages_cap = getenv("MG_STAGES") ? atoi(getenv("MG_STAGES")) : 0;
+    p.acc_cols = p.merged ? 2 * BN : BN;
     p.dbg = getenv("MG_DBG") ? atoi(getenv("MG_DBG")) : 0;
-    if (stages_cap > 0 && stages > stages_cap) stages = stages_cap;
-    p.stages = stages;
-    p.epi_off = stages * stage_bytes + 512;
-    p.idesc = a->a_fmt == 0 ? umma_idesc_tf32(128, BN) : umma_idesc_16(128, BN, a->a_fmt);
-    int tc = next_pow2(2 * BN);
+    const int stage_bytes = kABytes + BN * 128;
+    const int smem_avail = 227 * 1024 - 1024 - 512 - scratch_bytes;
+    size_t ring_bytes = 0;
+    if (halo) {
+        p.PW = halo_pw;
+        p.patch_tx = p.PW * (p.TH + 2) * 128;
+        p.patch_bytes = (p.patch_tx + 1023) & ~1023;
+        p.b_slot_bytes = p.acc_cols * 128;
+        p.n_items = p.kchunks * (p.merged ? 2 : 1);
+        p.a_slots = 2;
+        p.b_slots = (smem_avail - p.a_slots * p.patch_bytes) / p.b_slot_bytes;
+        if (p.b_slots > kMaxStages) {   // room to spare: deepen the patch ring first
+            p.a_slots = 3;
+            p.b_slots = (smem_avail - p.a_slots * p.patch_bytes) / p.b_slot_bytes;
+            if (p.b_slots > kMaxStages) p.b_slots = kMaxStages;
+        }
+        if (p.b_slots < 2) return set_error(-13, "mg_conv_igemm: halo rings do not fit shared memory");
+        ring_bytes = (size_t)p.a_slots * p.patch_bytes + (size_t)p.b_slots * p.b_slot_bytes;
+        p.stages = p.b_slots;
+    } else {
+        int stages = smem_avail / stage_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+        static const int stages_cap = getenv("MG_STAGES") ? atoi(getenv("MG_STAGES")) : 0;
+        if (stages_cap > 0 && stages > stages_cap) stages = stages_cap;
+        p.stages = stages;
+        ring_bytes = (size_t)stages * stage_bytes;
+    }
+    p.bar_off = (int)ring_bytes;
+    p.epi_off = (int)ring_bytes + 512;
+    p.idesc2 = a->a_fmt == 0 ? umma_idesc_tf32(128, BN) : umma_idesc_16(128, BN, a->a_fmt);
+    p.idesc = a->a_fmt == 0 ? umma_idesc_tf32(128, p.acc_cols) : umma_idesc_16(128, p.acc_cols, a->a_fmt);
+    int tc = next_pow2(2 * p.acc_cols);
     p.tmem_cols = tc < 32 ? 32 : tc;
     p.epi = a->epi; p.act = a->act; p.round_out = a->round_out;
     p.out = a->out; p.bias = a->bias;
@@ -632,6 +852,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         cuuint64_t strides[3] = {(cuuint64_t)a->Cin * esz, (cuuint64_t)a->W * a->Cin * esz,
                                  (cuuint64_t)a->H * a->W * a->Cin * esz};
         cuuint32_t box[4] = {(cuuint32_t)kelem, (cuuint32_t)(p.TW * a->stride), (cuuint32_t)(p.TH * a->stride), (cuuint32_t)p.TN};
+        if (halo) { box[1] = (cuuint32_t)p.PW; box[2] = (cuuint32_t)(p.TH + 2); box[3] = 1; }
         cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
         int rc = encode_tensor_map(&tmA, (void*)a->in, dt, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
@@ -648,7 +869,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         if (rc) return rc;
     }
 
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + scratch_bytes;
+    const size_t smem_bytes = ring_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + scratch_bytes;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -676,6 +897,17 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
 }
 
 }  // namespace mg
+
+// Debug: copy the 16 clock64() counters CTA 0 recorded during the last launch made with MG_DBG&16 (synchronises).
+// [0] producer total, [1] producer wait-empty, [2] MMA total, [3] MMA wait-tmem-empty, [4] MMA wait-full,
+// [5..8] epilogue warp 0: total, wait-tmem-full, busy, tiles; [9..12] same for epilogue warp 7.
+extern "C" int mg_debug_igemm_prof(unsigned long long* host16) {
+    if (!host16) return mg::set_error(-1, "mg_debug_igemm_prof: null pointer");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host16, mg::g_igemm_prof, 16 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return mg::set_error((int)e, "mg_debug_igemm_prof: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 extern "C" int mg_conv_igemm(const mg_igemm_args* a, void* stream) {
     return mg::igemm_launch(a, reinterpret_cast<cudaStream_t>(stream));

@@ -49,6 +49,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe of a phase (no hardware suspend): used for opportunistic prefetch decisions.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps (cudaErrorLaunchFailure) instead of hanging the GPU box.
 #ifndef MG_SPIN_LIMIT
 #define MG_SPIN_LIMIT (1u << 26)
@@ -175,6 +187,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                       // layout: SWIZZLE_128B
+    return d;
+}
+// General form: the operand's 8-row groups are `sbo_bytes` apart and the first row may sit anywhere inside a
+// 1024 B swizzle atom (start address a multiple of 128 B + a K advance < 128 B).  `base_offset` is the
+// descriptor's "matrix base offset" field (bits 49..51): (start_address >> 7) & 7 when the start is not
+// aligned to the 1024 B swizzle pattern.
+__device__ __forceinline__ uint64_t umma_desc_sw128_general(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_offset & 7) << 49;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 // Same, 32B swizzle: rows 32 B (8 tf32) apart, 8-row groups 256 B apart.

@@ -1,0 +1,59 @@
+// Microbenchmark: cycles per tcgen05.mma (cta_group::1, both operands in shared memory, K-major SW128) as a
+// function of M, N and operand kind, one CTA per SM, no TMA traffic (operands are whatever is in smem).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I michigan_b200/csrc tools/mma_rate.cu -o tools/bin/mma_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "mg_ptx.cuh"
+using namespace mg;
+
+__global__ void __launch_bounds__(128, 1) rate_kernel(int M, int N, int kind, int iters, int a_stride_slots, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (warp == 0 && lane == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 1) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = slot;
+    if (warp == 0 && lane == 0) {
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + 64 * 1024;
+        const uint32_t idesc = kind == 0 ? umma_idesc_tf32(M, N) : umma_idesc_16(M, N, 1);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            // rotate through 4 operand slots of 16 KB (A) / 32 KB (B) like a pipeline would
+            const uint32_t sa = a0 + (uint32_t)((it & 3) * a_stride_slots * 16384), sb = b0 + (uint32_t)((it & 1) * 32768);
+            const uint64_t da = umma_desc_kmajor_sw128(sa), db = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (kind == 0) umma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                else umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+            }
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+int main() {
+    long long* d; cudaMalloc(&d, 8);
+    cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int iters = 2000;
+    printf("kind   M    N   cycles/MMA   (ideal N/2 for M=128 f16 K16; tf32 K8)\n");
+    for (int kind = 0; kind < 2; ++kind)
+        for (int M : {128, 64})
+            for (int N : {256, 128, 64, 32}) {
+                if (M == 64 && N > 256) continue;
+                rate_kernel<<<148, 128, 180 * 1024>>>(M, N, kind, iters, 1, d);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long c = 0; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+                printf("%-5s %4d %4d   %8.1f   %s\n", kind == 0 ? "tf32" : "f16", M, N, (double)c / (iters * 4), e == cudaSuccess ? "" : cudaGetErrorString(e));
+            }
+    return 0;
+}

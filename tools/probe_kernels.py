@@ -290,6 +290,84 @@ def group_f16():
     report("SPADE fp16 GEMM -> bf16 hi+lo", nchw(hi.float() + lo.float()), ref, 3e-5)
 
 
+def group_halo(pw="16", bo="1"):
+    """Halo mode of the implicit GEMM (3x3 s1 p1: one input patch per K chunk, taps through shifted descriptors).
+    Run as halo_<PW>_<BO>; every case is also run with MG_HALO=0 and must agree with it bit for bit (same MMA order
+    per output element is not guaranteed, so only closeness to the reference is asserted)."""
+    os.environ["MG_HALO"] = "1"; os.environ["MG_HALO_PW"] = pw; os.environ["MG_HALO_BO"] = bo
+    print("halo mode PW=%s base-offset=%s" % (pw, bo))
+    igemm_case(2, 32, 32, 64, 64, 3, 1, 1)
+    igemm_case(1, 16, 16, 32, 32, 3, 1, 1)
+    igemm_case(2, 32, 32, 128, 256, 3, 1, 1)
+    igemm_case(1, 64, 40, 64, 128, 3, 1, 1, bn=64)       # ragged width (40 = 5 tiles of 8), two N tiles
+    igemm_case(2, 24, 20, 64, 64, 3, 1, 1)               # partial tiles in both directions
+    igemm_case(4, 128, 128, 128, 256, 3, 1, 1)           # many tiles per CTA: ring wrap, both TMEM buffers
+    g = torch.Generator(device="cpu").manual_seed(21)
+    for (N, h, Cin, Cout) in ((2, 32, 64, 64), (1, 64, 256, 128), (2, 48, 128, 256)):
+        x = torch.randn(N, Cin, h, h, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev)
+        b = torch.randn(Cout, generator=g).to(dev)
+        xh = nhwc(x).half()
+        ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+        got = ops.conv_igemm(xh, ops.pack_weight16(w, None, ops.F16, split=False), Cout, 3, 3, 1, 1, bias=b, a_fmt=ops.F16)
+        torch.cuda.synchronize()
+        report("halo fp16 1-pass N%d %d %d->%d" % (N, h, Cin, Cout), nchw(got), ref, 2e-5)
+        xn = nhwc(x)
+        hi = xn.bfloat16()
+        lo = (xn - hi.float()).bfloat16()
+        ref32 = F.conv2d(x, w, b, padding=1)
+        got = ops.conv_igemm(hi, ops.pack_weight16(w, None, ops.BF16, split=True), Cout, 3, 3, 1, 1, bias=b, a_fmt=ops.BF16, x_lo=lo)
+        torch.cuda.synchronize()
+        report("halo bf16 3-pass merged N%d %d %d->%d (vs fp32)" % (N, h, Cin, Cout), nchw(got), ref32, 6e-5)
+    C = 128
+    actv = torch.randn(2, 128, 32, 32, generator=g).to(dev).relu()
+    wg = (torch.randn(C, 128, 3, 3, generator=g) / 34.0).to(dev)
+    wb = (torch.randn(C, 128, 3, 3, generator=g) / 34.0).to(dev)
+    xs = torch.randn(2, C, 16, 16, generator=g).to(dev)
+    v1 = torch.ones(C, device=dev); v0 = torch.zeros(C, device=dev)
+    a16 = nhwc(actv).half()
+    gamma = F.conv2d(a16.float().permute(0, 3, 1, 2), wg.half().float(), None, padding=1)
+    beta = F.conv2d(a16.float().permute(0, 3, 1, 2), wb.half().float(), None, padding=1)
+    ref = F.leaky_relu(F.interpolate(xs, scale_factor=2, mode="nearest") * (1 + gamma) + beta, 0.2)
+    _, hi, lo = ops.conv_igemm(a16, ops.pack_weight_gb16(wg, wb), C, 3, 3, 1, 1, act=2, a_fmt=ops.F16,
+                               spade=(nhwc(xs), 1, v1, v0, v1, v0), out16=(ops.BF16, True), want_f32=False)
+    torch.cuda.synchronize()
+    report("halo SPADE fp16 GEMM -> bf16 hi+lo", nchw(hi.float() + lo.float()), ref, 3e-5)
+    # SPADE with the 3-pass bf16 gamma/beta GEMM (policy for feature maps <= 64)
+    ah = nhwc(actv).bfloat16(); al = (nhwc(actv) - ah.float()).bfloat16()
+    gamma = F.conv2d(actv, wg, None, padding=1); beta = F.conv2d(actv, wb, None, padding=1)
+    ref = F.leaky_relu(F.interpolate(xs, scale_factor=2, mode="nearest") * (1 + gamma) + beta, 0.2)
+    got = ops.conv_igemm(ah, ops.pack_weight_gb16(wg, wb, ops.BF16, True), C, 3, 3, 1, 1, act=2, a_fmt=ops.BF16, x_lo=al,
+                         spade=(nhwc(xs), 1, v1, v0, v1, v0))
+    torch.cuda.synchronize()
+    report("SPADE bf16 3-pass C128 (BN 256: classic path) (vs fp32)", nchw(got), ref, 6e-5)
+    C2 = 64
+    xs2 = xs[:, :C2].contiguous()
+    gamma = F.conv2d(actv, wg[:C2], None, padding=1); beta = F.conv2d(actv, wb[:C2], None, padding=1)
+    ref = F.leaky_relu(F.interpolate(xs2, scale_factor=2, mode="nearest") * (1 + gamma) + beta, 0.2)
+    got = ops.conv_igemm(ah, ops.pack_weight_gb16(wg[:C2].contiguous(), wb[:C2].contiguous(), ops.BF16, True), C2, 3, 3, 1, 1, act=2,
+                         a_fmt=ops.BF16, x_lo=al, spade=(nhwc(xs2), 1, v1[:C2].contiguous(), v0[:C2].contiguous(), v1[:C2].contiguous(), v0[:C2].contiguous()))
+    torch.cuda.synchronize()
+    report("halo SPADE bf16 3-pass merged C64 (vs fp32)", nchw(got), ref, 6e-5)
+    # timing at the benchmark shapes (halo on vs off)
+    for label, Cin, Cout, S, fmt in (("conv_0 up_3 bf16x3 128->64 512^2", 128, 64, 512, "bf3"), ("conv_1 up_3 bf16x3 64->64 512^2", 64, 64, 512, "bf3"),
+                                     ("conv_0 up_2 bf16x3 256->128 256^2", 256, 128, 256, "bf3"), ("tf32 128->64 512^2", 128, 64, 512, "tf32")):
+        x = torch.randn(8, S, S, Cin, device=dev)
+        w = torch.randn(Cout, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5
+        if fmt == "bf3":
+            hi = x.bfloat16(); lo = (x - hi.float()).bfloat16()
+            wp = ops.pack_weight16(w, None, ops.BF16, split=True)
+            f = lambda: ops.conv_igemm(hi, wp, Cout, 3, 3, 1, 1, a_fmt=ops.BF16, x_lo=lo)
+        else:
+            wp = ops.pack_weight(w, None, round_tf32=True)
+            f = lambda: ops.conv_igemm(x, wp, Cout, 3, 3, 1, 1)
+        for halo in ("1", "0"):
+            os.environ["MG_HALO"] = halo
+            print("perf %-36s halo=%s: %.3f ms" % (label, halo, _time(f)), flush=True)
+        del x
+    os.environ["MG_HALO"] = "1"
+
+
 def group_bwd():
     """tcgen05 weight gradient (MN-major operands, split-K) and data gradient (transposed conv)."""
     g = torch.Generator(device="cpu").manual_seed(31)
@@ -538,6 +616,11 @@ def group_perf():
 
 if __name__ == "__main__":
     grp = sys.argv[1]
+    if grp.startswith("halo_"):
+        _, pw, bo = grp.split("_")
+        group_halo(pw, bo)
+        print("== group %s done, failures: %s" % (grp, FAILS))
+        sys.exit(1 if FAILS else 0)
     t0 = time.time()
     print("== group %s on %s" % (grp, torch.cuda.get_device_name(0)), flush=True)
     globals()["group_" + grp]()

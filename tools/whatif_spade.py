@@ -33,4 +33,16 @@ for name, (f, wp) in variants.items():
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[2]
         print("%-5s MG_DBG=%2d  %.3f ms  %.0f TFLOP/s" % (name, dbg, ms, flops / ms / 1e9), flush=True)
+# cycle profile of CTA 0 (MG_DBG=16): who waits for whom
+import ctypes
+from michigan_b200 import _lib
+names = ["producer total", "producer wait-empty", "mma total", "mma wait-tmem-empty", "mma wait-full",
+         "epi0 total", "epi0 wait-tmem-full", "epi0 busy", "epi0 tiles", "epi7 total", "epi7 wait-tmem-full", "epi7 busy", "epi7 tiles"]
+for name, (f, wp) in variants.items():
+    for dbg in (16, 16 + 4, 16 + 3, 16 + 8, 16 + 32, 16 + 64):
+        os.environ["MG_DBG"] = str(dbg)
+        f(wp); f(wp)
+        buf = (ctypes.c_ulonglong * 16)()
+        _lib.check(_lib.load().mg_debug_igemm_prof(buf), "prof")
+        print("%s MG_DBG=%d cycles: " % (name, dbg) + ", ".join("%s %d" % (n, buf[i]) for i, n in enumerate(names)), flush=True)
 os.environ["MG_DBG"] = "0"
