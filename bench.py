@@ -88,13 +88,35 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def best_cpu_threads():
+    """The CPU arm gets every host thread it can USE: a 3x3 conv of the generator's shape is timed at several intra-op
+    thread counts (all cores down to 16) and the fastest is kept - on the 128-thread B200 hosts oversubscribing makes
+    PyTorch's CPU conv 3x slower than 16..32 threads (profiles/r01_cpu_threads.log)."""
+    import torch.nn.functional as F
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16)})
+    x = torch.randn(1, 128, 256, 256)
+    w = torch.randn(128, 128, 3, 3)
+    best, best_t = cands[-1], float("inf")
+    for t in cands:
+        torch.set_num_threads(t)
+        F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            F.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = t, dt
+    return best
+
+
 def cpu_generator_forward_ips(steps, warmup, sample_images=1):
     """The reference's generator forward restated on the CPU (oracle/michigan_oracle.py), all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import michigan_oracle as orc
     from helpers import preprocessed, reference_layout_state
-    cores = os.cpu_count() or 1
+    cores = best_cpu_threads()
     torch.set_num_threads(cores)
     cfg = dict(ngf=64, ndf=64, size=SIZE, batch=sample_images, data_seed=1234)
     sd = reference_layout_state("G", cfg, 0)
@@ -131,34 +153,49 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------ native arm
+# DRAM traffic of one launch of the dominant kernel from the `ncu --set full` capture committed as
+# profiles/r01_ncu_spade_gemm_f16_epilogue_v2.txt (dram__bytes_read.sum 809.4 MB + dram__bytes_write.sum 1027.4 MB at N=8);
+# algorithmic bytes = actv fp16 268 MB + x fp32 268 MB + weights 0.6 MB read, bf16 hi+lo 537 MB written.
+NCU_TRAFFIC_BYTES_N8 = 809.367296e6 + 1027.384e6
+
+
 def dominant_kernel_roofline(batch):
-    """Time the fused SPADE gamma/beta implicit GEMM of up_3.norm_0 alone: A = actv [N,512,512,128],
-    N_gemm = 2*128, K = 9*128, SPADE epilogue reading x [N,256,256,128] (upsample folded) and writing
-    h [N,512,512,128].  FLOPs per launch = 2 * N*512*512 * 1152 * 256 (SURVEY.md Appendix A rows
+    """Time the fused SPADE gamma/beta implicit GEMM of up_3.norm_0 alone, in the operand format the forward uses
+    (precision mode mixed16: fp16 operands, fp32 accumulate, bf16 hi/lo output; mode tf32: TF32 operands):
+    A = actv [N,512,512,128], N_gemm = 2*128, K = 9*128, SPADE epilogue reading x [N,256,256,128] (upsample folded)
+    and writing h [N,512,512,128].  FLOPs per launch = 2 * N*512*512 * 1152 * 256 (SURVEY.md Appendix A rows
     G.up_3.norm_0.mlp_gamma + mlp_beta = 2 * 77.309 GFLOP per image)."""
-    from michigan_b200 import ops
+    from michigan_b200 import ops, precision
     dev = "cuda"
     actv = torch.randn(batch, SIZE, SIZE, 128, device=dev)
     wg = torch.randn(128, 128, 3, 3, device=dev) / 34
-    wp = ops.pack_weight_gb(wg, wg)
     xs = torch.randn(batch, SIZE // 2, SIZE // 2, 128, device=dev)
     v = torch.ones(128, device=dev)
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
-    args = dict(act=2, round_out=True, spade=(xs, 1, v, v, v, v))
+    if precision.mode() == "tf32":
+        wp = ops.pack_weight_gb(wg, wg)
+        kind = "kind::tf32"
+        f = lambda: ops.conv_igemm(actv, wp, 128, 3, 3, 1, 1, act=2, round_out=True, spade=(xs, 1, v, v, v, v))
+    else:
+        a16 = actv.half()
+        wp = ops.pack_weight_gb16(wg, wg)
+        kind = "kind::f16"
+        f = lambda: ops.conv_igemm(a16, wp, 128, 3, 3, 1, 1, act=2, a_fmt=ops.F16, spade=(xs, 1, v, v, v, v),
+                                   out16=(ops.BF16, True), want_f32=False)
     for _ in range(3):
-        ops.conv_igemm(actv, wp, 128, 3, 3, 1, 1, **args)
+        f()
     times = []
     for _ in range(5):
         flush.zero_()  # evict L2 (126 MB) between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv_igemm(actv, wp, 128, 3, 3, 1, 1, **args)
+        f()
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     ms = sorted(times)[len(times) // 2]
     flops = 2.0 * batch * SIZE * SIZE * 1152 * 256
-    return flops / (ms * 1e-3) / 1e12, ms, flops
+    return flops / (ms * 1e-3) / 1e12, ms, flops, kind
 
 
 def run_native(a):
@@ -244,14 +281,15 @@ def run_native(a):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        tf, kms, kflops = dominant_kernel_roofline(batch)
+        tf, kms, kflops, kkind = dominant_kernel_roofline(batch)
+        from michigan_b200 import precision
         peak_tf = float(pk["bf16_tflops"])
         ms_step = ms_total / a.steps
         value = world * batch * a.steps / (ms_total * 1e-3)
         line = {
             "metric": "512x512 images/sec (generator forward)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": DTYPE_NOTE[precision.mode()], "data": "synthetic",
             "config": {"workload": "generator-only forward (netG=spadeb ngf64, 109.5M params, train-mode statistics, no grad), "
                                    "batch %d/GPU, 512x512 synthetic mask/orient/ref inputs" % batch,
                        "global_batch": batch * world, "parallelism": "dp%d" % world,
@@ -262,10 +300,13 @@ def run_native(a):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "igemm_tf32_kernel (fused SPADE gamma|beta GEMM + modulate + LeakyReLU, up_3.norm_0 shape)",
+            "roofline": {"kernel": "igemm_tf32_kernel<1> (fused SPADE gamma|beta implicit GEMM + modulate + LeakyReLU, up_3.norm_0 shape, "
+                                   "tcgen05 %s)" % kkind,
                          "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": None, "peak_kind": "%s bf16 dense burst (MEASURED_PEAKS.json); kind::tf32 issues at half "
-                                                         "the bf16 rate, i.e. frac vs TF32 peak = %.2f" % (pk_kind, 2 * tf / peak_tf),
+                         "traffic": NCU_TRAFFIC_BYTES_N8 * batch / 8 if kkind == "kind::f16" else None,
+                         "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01_ncu_spade_gemm_f16_*.txt)",
+                         "peak_kind": "%s bf16 dense burst (MEASURED_PEAKS.json)%s" % (
+                             pk_kind, "; kind::tf32 issues at half the bf16 rate" if kkind == "kind::tf32" else ""),
                          "ms_per_launch": kms, "flops_per_launch": kflops},
         }
         if not a.no_cpu_baseline and world == 1:
@@ -276,6 +317,11 @@ def run_native(a):
     if world > 1:
         dist.destroy_process_group()
 
+
+DTYPE_NOTE = {
+    "mixed16": "fp16/bf16 tensor-core operands (bf16 hi+lo split where needed), fp32 accumulate and storage",
+    "tf32": "tf32",
+}
 
 TRAIN_GFLOP_PER_IMG = 4775.8  # G step + D step, hinge GAN + GAN-feature losses
 

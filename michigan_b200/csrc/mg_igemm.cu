@@ -118,7 +118,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align the operand ring (SWIZZLE_128B atoms are 1024 B).
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = kABytes + p.BN * 128;
+    const int stage_bytes = kABytes + p.acc_cols * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
     uint64_t* full_bar = bars;                        // halo mode: the weight (B) ring
     uint64_t* empty_bar = bars + kMaxStages;
@@ -278,7 +278,6 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             long long w_empty = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const bool ldA = !(p.dbg & 2) || tile == (int)blockIdx.x, ldB = !(p.dbg & 1) || tile == (int)blockIdx.x;
-                const uint32_t tx = (ldA ? kABytes : 0) + (ldB ? p.BN * 128 : 0);
                 const int nt = tile % p.n_tiles;
                 const int m = tile / p.n_tiles;
                 const int tw = m % p.tiles_w;
@@ -287,23 +286,29 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int iw0 = tw * p.TW * p.stride - p.pad_w;
                 const int ih0 = th * p.TH * p.stride - p.pad_h;
                 const int n0 = tn * p.TN;
-                const int bparts = p.parts == 3 ? 2 : 1;   // weight operand holds (hi) or (hi, lo) per tap
+                const int bparts = p.parts >= 2 ? 2 : 1;   // weight operand holds (hi) or (hi, lo) per tap
                 for (int tap = 0; tap < p.KH * p.KW; ++tap) {
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
                     for (int part = 0; part < p.parts; ++part) {
-                        // split precision: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
+                        // split precision, 3 passes: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
+                        // merged (2 passes): A_hi x [W_hi ; W_lo] (N = 2*BN) + A_lo x W_hi (N = BN)
                         const CUtensorMap* ta = part == 1 ? &tmA2 : &tmA;
                         const int bsel = part == 2 ? 1 : 0;
+                        const bool both = p.merged && part == 0;
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             const long long t0 = prof ? clock64() : 0;
                             mbar_wait(&empty_bar[st], ph ^ 1);
                             if (prof) w_empty += clock64() - t0;
                             uint8_t* sa = smem + (size_t)st * stage_bytes;
-                            if (tx == 0) { mbar_arrive(&full_bar[st]); }
-                            else mbar_arrive_expect_tx(&full_bar[st], tx);
+                            const uint32_t txs = (ldA ? kABytes : 0) + (ldB ? p.BN * 128 * (both ? 2 : 1) : 0);
+                            if (txs == 0) { mbar_arrive(&full_bar[st]); }
+                            else mbar_arrive_expect_tx(&full_bar[st], txs);
                             if (ldA) tma_load_4d(sa, ta, &full_bar[st], kc * p.kelem, iw0 + kw, ih0 + kh, n0);
-                            if (ldB) tma_load_2d(sa + kABytes, &tmB, &full_bar[st], (tap * bparts + bsel) * p.Cin + kc * p.kelem,
-                                                 nt * p.BN);
+                            const int kofs = (tap * bparts + bsel) * p.Cin + kc * p.kelem;
+                            if (ldB) {
+                                tma_load_2d(sa + kABytes, &tmB, &full_bar[st], kofs, nt * p.BN);
+                                if (both) tma_load_2d(sa + kABytes + p.BN * 128, &tmB, &full_bar[st], kofs + p.Cin, nt * p.BN);
+                            }
                             if (++st == p.stages) { st = 0; ph ^= 1; }
                         }
                     }
@@ -334,13 +339,15 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
                     const uint64_t db = umma_desc_kmajor_sw128(sa + kABytes);
+                    // merged split precision: k-steps alternate (per K-chunk run) between N = 2*BN and N = BN
+                    const uint32_t idesc = (p.merged && ((ks / p.kchunks) & 1)) ? p.idesc2 : p.idesc;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in 16 B units
                         if (p.a_fmt == 0)
-                            umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ks | k) != 0 ? 1u : 0u);
+                            umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
                         else
-                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ks | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[st]);  // frees the smem stage when these MMAs retire
                     if (++st == p.stages) { st = 0; ph ^= 1; }
@@ -775,13 +782,17 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.bo_mode = getenv("MG_HALO_BO") ? atoi(getenv("MG_HALO_BO")) : 0;
     bool halo = halo_env && p.epi_impl == 1 && a->KH == 3 && a->KW == 3 && a->stride == 1 && p.pad_h == 1 && p.pad_w == 1 &&
                 a->OH >= 16 && a->OW >= 8 && a->H == a->OH && a->W == a->OW && (halo_pw == 10 || halo_pw == 16);
-    if (halo && a->split) {
-        // merged split precision: A_hi x [W_hi ; W_lo] (N = 2*BN) + A_lo x W_hi (N = BN); accumulator = 2*BN columns
-        if (a->BN == 0 && BN > 128) BN = 128;
-        if (BN > 128 || coutg % BN != 0) halo = false;
-    }
+    // merged split precision: A_hi x [W_hi ; W_lo] (N = 2*BN) + A_lo x W_hi (N = BN): two MMAs per K step instead of
+    // three (every tcgen05.mma costs >= ~100 cycles whatever its N, profiles/r01_mma_rate_microbench.log); the
+    // accumulator is 2*BN columns wide and the epilogue adds the halves.  MG_MERGE=0 restores the 3-pass form.
+    const int merge_env = getenv("MG_MERGE") ? atoi(getenv("MG_MERGE")) : 1;
+    bool merged = false;
+    // Only where the GEMM N is thin anyway (<= 128): for wider layers three N = 256 passes beat two passes over
+    // twice as many N = 128 tiles (measured: 512->512 at 64^2 0.39 ms 3-pass vs 0.52 ms merged).
+    if (a->split && merge_env && p.epi_impl == 1 && BN <= 128) merged = true;
+    if (halo && a->split && !merged) halo = false;
     p.halo = halo ? 1 : 0;
-    p.merged = (halo && a->split) ? 1 : 0;
+    p.merged = merged ? 1 : 0;
     if (halo) { p.TW = 8; p.TH = 16; p.TN = 1; }
     else {
         p.TW = next_pow2(a->OW) < 16 ? next_pow2(a->OW) : 16;
@@ -796,11 +807,11 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.n_tiles = coutg / BN;
     p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
     p.kchunks = a->Cin / kelem;
-    p.a_fmt = a->a_fmt; p.parts = a->split ? 3 : 1; p.kelem = kelem;
+    p.a_fmt = a->a_fmt; p.parts = merged ? 2 : (a->split ? 3 : 1); p.kelem = kelem;
     p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
     p.acc_cols = p.merged ? 2 * BN : BN;
     p.dbg = getenv("MG_DBG") ? atoi(getenv("MG_DBG")) : 0;
-    const int stage_bytes = kABytes + BN * 128;
+    const int stage_bytes = kABytes + p.acc_cols * 128;
     const int smem_avail = 227 * 1024 - 1024 - 512 - scratch_bytes;
     size_t ring_bytes = 0;
     if (halo) {

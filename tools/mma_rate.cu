@@ -7,7 +7,8 @@
 #include "mg_ptx.cuh"
 using namespace mg;
 
-__global__ void __launch_bounds__(128, 1) rate_kernel(int M, int N, int kind, int iters, int a_stride_slots, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int M, int N, int kind, int iters, int a_stride_slots, long long* out,
+                                                      int a_row_off, int a_sbo, int b_row_off, int b_sbo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -25,7 +26,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int M, int N, int kind, in
         for (int it = 0; it < iters; ++it) {
             // rotate through 4 operand slots of 16 KB (A) / 32 KB (B) like a pipeline would
             const uint32_t sa = a0 + (uint32_t)((it & 3) * a_stride_slots * 16384), sb = b0 + (uint32_t)((it & 1) * 32768);
-            const uint64_t da = umma_desc_kmajor_sw128(sa), db = umma_desc_kmajor_sw128(sb);
+            // halo-style operands: first row shifted by *_row_off rows (128 B each), 8-row groups *_sbo bytes apart
+            const uint64_t da = umma_desc_sw128_general(sa + a_row_off * 128, a_sbo, 0), db = umma_desc_sw128_general(sb + b_row_off * 128, b_sbo, 0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (kind == 0) umma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
@@ -50,10 +52,21 @@ int main() {
         for (int M : {128, 64})
             for (int N : {256, 128, 64, 32}) {
                 if (M == 64 && N > 256) continue;
-                rate_kernel<<<148, 128, 180 * 1024>>>(M, N, kind, iters, 1, d);
+                rate_kernel<<<148, 128, 180 * 1024>>>(M, N, kind, iters, 1, d, 0, 1024, 0, 1024);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long c = 0; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
                 printf("%-5s %4d %4d   %8.1f   %s\n", kind == 0 ? "tf32" : "f16", M, N, (double)c / (iters * 4), e == cudaSuccess ? "" : cudaGetErrorString(e));
             }
+    printf("\nshifted / strided operands (f16, M=128): a_row_off a_sbo b_row_off b_sbo N -> cycles/MMA\n");
+    const int cfg[][4] = {{0, 1024, 0, 1024}, {1, 1024, 0, 1024}, {0, 1280, 0, 1024}, {1, 1280, 0, 1024}, {0, 2048, 0, 1024}, {1, 2048, 0, 1024},
+                          {0, 1024, 1, 1024}, {0, 1024, 0, 1280}, {0, 1024, 1, 1280}, {0, 1024, 1, 2048}, {0, 1024, 11, 1280}};
+    for (auto& c4 : cfg)
+        for (int N : {256, 128, 64}) {
+            if (c4[3] != 1024 && N * c4[3] / 8 + 4096 > 64 * 1024) continue;   // stay inside the smem window
+            rate_kernel<<<148, 128, 180 * 1024>>>(128, N, 1, iters, 1, d, c4[0], c4[1], c4[2], c4[3]);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long c = 0; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+            printf("%2d %5d %2d %5d  N=%3d   %8.1f   %s\n", c4[0], c4[1], c4[2], c4[3], N, (double)c / (iters * 4), e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
     return 0;
 }
