@@ -362,8 +362,10 @@ def run_train_step(a, rank, world, local):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(a.steps):
         step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / a.steps   # CPU time to issue one step (no sync inside)
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0
@@ -389,7 +391,7 @@ def run_train_step(a, rank, world, local):
             "achieved_tflops_step": TRAIN_GFLOP_PER_IMG * a.batch / ms_step,
             # the step already starts from host (pinned) tensors and returns host-visible loss scalars
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(losses)},
-            "gpu_launches": launches, "clocks": clocks, "losses": losses,
+            "gpu_launches": launches, "clocks": clocks, "losses": losses, "host_enqueue_ms_per_step": host_enqueue_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

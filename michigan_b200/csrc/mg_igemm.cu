@@ -111,7 +111,8 @@ __device__ __forceinline__ void store16(const IgemmParams& p, const float (&y)[1
 // SPEC selects a compile-time specialisation of the (instruction-bound) epilogue:
 //   0 generic (everything decided at run time)
 //   1 SPADE + LeakyReLU -> bf16 hi/lo operand only      2 SPADE + no activation -> bf16 hi/lo operand only
-template <int SPEC>
+// CW: channels per epilogue chunk (16 or 32), compile time so that the per-chunk register arrays are sized exactly.
+template <int SPEC, int CW>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
@@ -369,7 +370,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int half = ew >> 2;
-        float* scr = reinterpret_cast<float*>(smem + p.epi_off) + ew * (32 * 36);
+        float* scr = reinterpret_cast<float*>(smem + p.epi_off) + ew * (32 * (CW + 4));
         constexpr bool kS = SPEC == 1 || SPEC == 2;
         const bool spade = kS ? true : (p.epi == 1);
         const int act = SPEC == 1 ? 2 : (SPEC == 2 ? 0 : p.act);
@@ -380,9 +381,9 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool has_aux = kS ? false : (p.aux != nullptr);
         const bool do_round = kS ? false : (p.round_out != 0);
         const int span = spade ? (p.BN >> 2) : (p.BN >> 1);   // channels this warp owns per tile
-        const int cw = (span % 32 == 0 && !p.epi_cw16) ? 32 : 16;
-        const int rs = cw + 4;
-        const int lpp = cw >> 2, ppp = 32 / lpp, passes = lpp;
+        constexpr int cw = CW;
+        constexpr int rs = cw + 4;
+        constexpr int lpp = cw >> 2, ppp = 32 / lpp, passes = lpp;   // lanes per pixel, pixels per pass, passes per chunk
         const int q = lane % lpp, psub = lane / lpp;
         const int twl = 31 - __clz(p.TW), thl = 31 - __clz(p.TH);
         const int ch_tile = p.BN >> 1;
@@ -398,12 +399,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int th = (m / p.tiles_w) % p.tiles_h;
             const int tn = m / m_tiles_per_img;
             // per-tile pixel bookkeeping for the (up to 8) pixels this lane serves in the transposed domain
-            uint32_t pixo[8], srco[8];
+            uint32_t pixo[passes], srco[passes];
             uint32_t vmask = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < passes; ++j) {
                 pixo[j] = srco[j] = 0;
-                if (j >= passes) continue;
                 const int r = quarter * 32 + j * ppp + psub;
                 const int ow = tw * p.TW + (r & (p.TW - 1));
                 const int oh = th * p.TH + ((r >> twl) & (p.TH - 1));
@@ -422,40 +422,61 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int cb = 0; cb < span; cb += cw) {
                 if (p.dbg & 4) break;
                 const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
-                float4 av[8], bv[8], pre[8];
+                float4 av[passes], bv[passes], pre[passes];
                 const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
-                // Issue the per-pixel side loads (SPADE: the tensor being normalised; else the residual) FIRST so that
-                // their L2 latency overlaps the TMEM -> scratch -> register transposition below.
-                const float* side = spade ? p.x : p.res;
-                if (side != nullptr && cch < p.Cout && !(p.dbg & (8 | 64))) {
+                // TMEM chunk -> registers: ALL tcgen05.ld of the chunk (gamma and beta halves) are issued back to back and
+                // waited for once - under a running MMA stream one ld+wait round trip costs ~1000 cycles, so the old
+                // load/wait-per-16-columns order serialised eight of them per tile.
+                uint32_t g0[16], g1[16], b0[16], b1[16];
+                // registers (row per lane) -> scratch -> registers (transposed: lanes cover contiguous channels)
+                auto transpose = [&](const uint32_t (&v0)[16], const uint32_t (&v1)[16], float4 (&dst)[passes], bool add) {
+                    float4* d = reinterpret_cast<float4*>(scr + lane * rs);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if ((vmask >> j) & 1u) pre[j] = __ldg(reinterpret_cast<const float4*>(side + (size_t)srco[j] * p.Cout + cch));
-                }
-                // TMEM chunk -> scratch (row per lane) -> registers (transposed: lanes cover contiguous channels)
-                auto load_chunk = [&](int colbase, float4 (&dst)[8], bool add) {
-                    for (int s0 = 0; s0 < cw; s0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(t_row + (uint32_t)(colbase + s0), v);
-                        tmem_ld_wait();
-                        float4* d = reinterpret_cast<float4*>(scr + lane * rs + s0);
+                    for (int i = 0; i < 4; ++i)
+                        d[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]), __uint_as_float(v0[4 * i + 2]),
+                                           __uint_as_float(v0[4 * i + 3]));
+                    if (cw == 32) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            d[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                               __uint_as_float(v[4 * i + 3]));
+                            d[4 + i] = make_float4(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]), __uint_as_float(v1[4 * i + 2]),
+                                                   __uint_as_float(v1[4 * i + 3]));
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < passes) {
-                            const float4 t = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
-                            if (add) { dst[j].x += t.x; dst[j].y += t.y; dst[j].z += t.z; dst[j].w += t.w; }
-                            else dst[j] = t;
-                        }
+                    for (int j = 0; j < passes; ++j) {
+                        const float4 t = *reinterpret_cast<const float4*>(scr + (j * ppp + psub) * rs + q * 4);
+                        if (add) { dst[j].x += t.x; dst[j].y += t.y; dst[j].z += t.z; dst[j].w += t.w; }
+                        else dst[j] = t;
+                    }
                     __syncwarp();
                 };
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = bias4, sh4 = bias4, g14 = bias4, bb4 = bias4;
+                auto load_chunk = [&](int colbase, float4 (&dst)[passes], bool add) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(t_row + (uint32_t)colbase, v0);
+                    if (cw == 32) tmem_ld16(t_row + (uint32_t)(colbase + 16), v1);
+                    tmem_ld_wait();
+                    transpose(v0, v1, dst, add);
+                };
+                tmem_ld16(t_row + (uint32_t)col, g0);
+                if (cw == 32) tmem_ld16(t_row + (uint32_t)(col + 16), g1);
+                if (spade) {
+                    tmem_ld16(t_row + (uint32_t)(col + ch_tile), b0);
+                    if (cw == 32) tmem_ld16(t_row + (uint32_t)(col + ch_tile + 16), b1);
+                }
+                tmem_ld_wait();
                 const bool ch_ok = cch < p.Cout;
+                transpose(g0, g1, av, false);
+                // Per-pixel side loads (SPADE: the tensor being normalised; else the residual): issued as soon as the first
+                // transposition has freed its registers, so their L2 latency overlaps the second one.
+                const float* side = spade ? p.x : p.res;
+                if (side != nullptr && ch_ok && !(p.dbg & (8 | 64))) {
+#pragma unroll
+                    for (int j = 0; j < passes; ++j)
+                        if ((vmask >> j) & 1u) pre[j] = __ldg(reinterpret_cast<const float4*>(side + (size_t)srco[j] * p.Cout + cch));
+                }
+                if (p.merged) load_chunk(col + p.BN, av, true);   // split precision, merged N: + A_hi * W_lo columns
+                if (spade) transpose(b0, b1, bv, false);
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = bias4, sh4 = bias4, g14 = bias4, bb4 = bias4;
                 if (ch_ok) {
                     if (spade) {
                         sc4 = __ldg(reinterpret_cast<const float4*>(p.nscale + cch));
@@ -466,13 +487,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + cch));
                     }
                 }
-                load_chunk(col, av, false);
-                if (p.merged) load_chunk(col + p.BN, av, true);   // split precision, merged N: + A_hi * W_lo columns
                 if (spade) {
                     // fold gamma into the normalised input right away (frees `pre` before beta is fetched):
                     // av <- (x * rstd + shift) * (1 + gamma)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < passes; ++j) {
                         if (!((vmask >> j) & 1u) || !ch_ok) continue;
                         const float4 xv = (p.dbg & (8 | 64)) ? sc4 : pre[j];
                         const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
@@ -480,12 +499,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         av[j] = make_float4(fmaf(xv.x, sc4.x, sh4.x) * gs.x, fmaf(xv.y, sc4.y, sh4.y) * gs.y,
                                             fmaf(xv.z, sc4.z, sh4.z) * gs.z, fmaf(xv.w, sc4.w, sh4.w) * gs.w);
                     }
-                    load_chunk(col + ch_tile, bv, false);
                     if (p.merged) load_chunk(col + ch_tile + p.BN, bv, true);
                 }
                 if (!ch_ok) continue;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < passes; ++j) {
                     if (!((vmask >> j) & 1u)) continue;
                     const size_t pix = pixo[j];
                     float y[4];
@@ -768,9 +786,16 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     static const int epi_impl_bias = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
     static const int epi_impl_spade = getenv("MG_EPI_IMPL_SPADE") ? atoi(getenv("MG_EPI_IMPL_SPADE")) : epi_impl_bias;
     const int epi_impl_env = a->epi == MG_EPI_SPADE ? epi_impl_spade : epi_impl_bias;
-    static const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 0;
+    // epilogue chunk width: 16 channels (no register spills) unless MG_EPI_CW16=0 / MG_EPI_CW_SPADE=32 ask for 32
+    const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 1;
     p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
-    const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * 36 * 4 : 0;
+    // epilogue chunk width (channels per TMEM->scratch->register round): 16 everywhere by default (no register spills,
+    // 20 KB of scratch => one more pipeline stage at BN = 256); MG_EPI_CW16=0 / MG_EPI_CW_SPADE=32 select 32 where possible.
+    const int span_epi = a->epi == MG_EPI_SPADE ? (BN >> 2) : (BN >> 1);
+    const int cw_spade = getenv("MG_EPI_CW_SPADE") ? atoi(getenv("MG_EPI_CW_SPADE")) : 16;
+    int cw = (span_epi % 32 == 0 && !p.epi_cw16) ? 32 : 16;
+    if (a->epi == MG_EPI_SPADE) cw = (cw_spade == 32 && span_epi % 32 == 0) ? 32 : 16;
+    const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * (cw + 4) * 4 : 0;
     // Halo mode: 3x3 / stride 1 / pad 1 convolutions (the SPADE gamma|beta GEMMs, conv_0/conv_1 and their dgrads) load
     // one [PW x (TH+2)] input patch per K chunk and read the 9 taps out of it through shifted UMMA descriptors.
     // MG_HALO: 0 off (default: measured no faster on B200 - these kernels are bound by the MMA operand fetch / epilogue,
@@ -885,9 +910,11 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_set_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaSuccess;
+        const void* kernels[6] = {(const void*)igemm_tf32_kernel<0, 16>, (const void*)igemm_tf32_kernel<0, 32>, (const void*)igemm_tf32_kernel<1, 16>,
+                                  (const void*)igemm_tf32_kernel<1, 32>, (const void*)igemm_tf32_kernel<2, 16>, (const void*)igemm_tf32_kernel<2, 32>};
+        for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+            e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set_dev = dev;
     }
@@ -898,9 +925,11 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     if (p.epi_impl == 1 && a->epi == MG_EPI_SPADE && !a->out && a->out_hi && a->out_lo && a->out16_fmt == 2 && !a->aux_out &&
         !a->round_out && (a->act == MG_ACT_LRELU || a->act == MG_ACT_NONE))
         spec = a->act == MG_ACT_LRELU ? 1 : 2;
-    if (spec == 1) igemm_tf32_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
-    else if (spec == 2) igemm_tf32_kernel<2><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
-    else igemm_tf32_kernel<0><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
+#define MG_LAUNCH(S, C) igemm_tf32_kernel<S, C><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p)
+    if (spec == 1) { if (cw == 32) MG_LAUNCH(1, 32); else MG_LAUNCH(1, 16); }
+    else if (spec == 2) { if (cw == 32) MG_LAUNCH(2, 32); else MG_LAUNCH(2, 16); }
+    else { if (cw == 32) MG_LAUNCH(0, 32); else MG_LAUNCH(0, 16); }
+#undef MG_LAUNCH
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, "igemm launch: %s", cudaGetErrorString(e));
