@@ -137,6 +137,12 @@ typedef struct mg_thin_args {
 } mg_thin_args;
 int mg_conv_thin(const mg_thin_args* a, void* stream);
 int mg_pack_weight_thin(const float* w_oihw, float* wt, int O, int I, int CinP, int KH, int KW, void* stream);
+/* SPADE mlp_shared (normalization.py:92-96: Conv2d(label_nc=4, 128, 3, padding=1) + ReLU on the nearest-resized segmap,
+ * normalization.py:110-111) as ONE K=128 tensor-core GEMM per 128-pixel tile: bf16 hi/lo split of the 3x3x4 patch and of the
+ * weights concatenated along K.  Same mg_thin_args contract as mg_conv_thin restricted to CinP 4, 3x3, stride 1, pad 1,
+ * Cout 128; a->w is the bf16 [128][128] operand written by mg_pack_weight_seg_tc. */
+int mg_conv_seg_tc(const mg_thin_args* a, void* stream);
+int mg_pack_weight_seg_tc(const float* w_oihw, void* wpack_bf16, int O, int I, void* stream);
 
 /* conv_img: tanh(conv3x3(lrelu(x))) 64->3, NHWC in, NCHW out (generator.py:227-228). */
 int mg_conv_img(const float* x, const float* w_oihw, const float* bias, float* out_nchw, int N, int H, int W,

@@ -64,6 +64,8 @@ SIGNATURES = {
     "mg_pack_weight_gb16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_thin": [C.POINTER(ThinArgs), _p],
     "mg_pack_weight_thin": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mg_conv_seg_tc": [C.POINTER(ThinArgs), _p],
+    "mg_pack_weight_seg_tc": [_p, _p, _i, _i, _p],
     "mg_conv_img": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_to1": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_bn_stats": [_p, _ll, _i, _p, _p],

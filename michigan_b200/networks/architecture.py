@@ -70,8 +70,8 @@ class SPADEResnetBlock(nn.Module):
         else:
             wgb = c.get((name + ".gb16", gfmt, gsplit), [sp.mlp_gamma.weight, sp.mlp_beta.weight],
                         lambda: ops.pack_weight_gb16(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach(), gfmt, gsplit))
-        wsh = c.get(name + ".sh", [sp.mlp_shared[0].weight],
-                    lambda: ops.pack_weight_thin(sp.mlp_shared[0].weight.detach(), 4))
+        wsh = c.get((name + ".sh", ops.seg_tc_enabled()), [sp.mlp_shared[0].weight],
+                    lambda: ops.pack_mlp_shared(sp.mlp_shared[0].weight.detach()))
         g1 = c.get(name + ".g1", [sp.mlp_gamma.bias], lambda: (sp.mlp_gamma.bias.detach() + 1.0).contiguous())
         return wsh, sp.mlp_shared[0].bias.detach(), wgb, g1, sp.mlp_beta.bias.detach()
 
@@ -100,7 +100,7 @@ class SPADEResnetBlock(nn.Module):
             cfmt = precision.conv_fmt(src.shape[-1])
             wsh, bsh, wgb, g1, bb = self._spade_pack(name, gfmt, gsplit)
             kw_a, get_a = precision.out_spec(gfmt, gsplit)
-            actv = get_a(ops.conv_thin(seg4, wsh, bsh, 128, 3, 3, 1, 1, seg_resize=R, act=ops.ACT_RELU, out_hw=(h, w), **kw_a))
+            actv = get_a(ops.mlp_shared(seg4, wsh, bsh, seg_resize=R, act=ops.ACT_RELU, out_hw=(h, w), **kw_a))
             c = src.shape[-1]
             kw_h, get_h = precision.out_spec(cfmt, cfmt == ops.BF16)
             return get_h(precision.conv(actv, wgb, c, 3, 3, 1, 1, act=act, spade=(src, shift, nscale, nshift, g1, bb), **kw_h))

@@ -87,8 +87,8 @@ def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_
 # =============================================================================================== SPADE + conv
 def _spade_fwd(blk, name, src, shift, ns, nh, act, seg4, R, hw):
     sp = getattr(blk, name)
-    wsh = ops.pack_weight_thin(sp.mlp_shared[0].weight.detach(), 4)
-    actv = ops.conv_thin(seg4, wsh, sp.mlp_shared[0].bias.detach(), 128, 3, 3, 1, 1, seg_resize=R, act=_RELU, round_out=True, out_hw=hw)
+    wsh = ops.pack_mlp_shared(sp.mlp_shared[0].weight.detach())
+    actv = ops.mlp_shared(seg4, wsh, sp.mlp_shared[0].bias.detach(), seg_resize=R, act=_RELU, round_out=True, out_hw=hw)
     c = src.shape[-1]
     g1 = torch.empty((src.shape[0], hw[0], hw[1], c), device=src.device, dtype=torch.float32)
     wgb = ops.pack_weight_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach())
@@ -106,8 +106,7 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     del dh
     sp = S.sp
     c = S.src.shape[-1]
-    actv = ops.conv_thin(seg4, S.wsh, sp.mlp_shared[0].bias.detach(), 128, 3, 3, 1, 1, seg_resize=S.R, act=_RELU, round_out=True,
-                         out_hw=S.hw)
+    actv = ops.mlp_shared(seg4, S.wsh, sp.mlp_shared[0].bias.detach(), seg_resize=S.R, act=_RELU, round_out=True, out_hw=S.hw)
     dwg, dwb = ops.unpack_wgrad_gb(ops.conv_wgrad(dgb, actv, 3, 3, 1, 1), c, 128)
     G.add(sp.mlp_gamma.weight, dwg)
     G.add(sp.mlp_beta.weight, dwb)

@@ -6,6 +6,8 @@ libmichigan_sm100.so.  Activations are NHWC fp32 ([N,H,W,C] contiguous).
 import ctypes as C
 import math
 
+import os
+
 import torch
 
 from . import _lib
@@ -197,6 +199,58 @@ def conv_thin(x, wt, bias, cout, kh, kw, stride=1, pad=0, *, pad_mode=0, seg_res
     if out16 is not None:
         return out, hi, lo
     return out
+
+
+def pack_weight_seg_tc(w_oihw):
+    """bf16 [128][128] operand of conv_seg_tc: k = part*36 + tap*4 + ci with parts (W_hi, W_hi, W_lo)."""
+    _chk(w_oihw, "w")
+    O, I, KH, KW = w_oihw.shape
+    assert KH == 3 and KW == 3
+    out = torch.empty((O, 128), device=w_oihw.device, dtype=torch.bfloat16)
+    check(_lib.load().mg_pack_weight_seg_tc(_p(w_oihw), _p(out), O, I, _stream()), "mg_pack_weight_seg_tc")
+    return out
+
+
+def conv_seg_tc(seg4, wpack, bias, *, seg_resize=0, act=ACT_RELU, round_out=False, out_hw=None, out16=None, want_f32=True):
+    """SPADE mlp_shared (4 -> 128, 3x3, pad 1, + act) on tensor cores; same results contract as conv_thin."""
+    _chk(seg4, "seg4"); _chk(wpack, "wpack", torch.bfloat16); _chk(bias, "bias")
+    N, Hp, Wp, CinP = seg4.shape
+    H, W = out_hw if seg_resize else (Hp, Wp)
+    out = torch.empty((N, H, W, 128), device=seg4.device, dtype=torch.float32) if want_f32 else None
+    hi, lo = _alloc16((N, H, W, 128), seg4.device, out16)
+    a = ThinArgs()
+    a.inp, a.w, a.bias, a.out = _p(seg4), _p(wpack), _p(bias), _p(out)
+    a.out_hi, a.out_lo, a.out16_fmt = _p(hi), _p(lo), (out16[0] if out16 else 0)
+    a.N, a.H, a.W, a.CinP = N, H, W, CinP
+    a.OH, a.OW, a.Cout = H, W, 128
+    a.KH, a.KW, a.stride, a.pad = 3, 3, 1, 1
+    a.pad_mode, a.seg_resize = 0, seg_resize
+    a.act, a.round_out = act, int(round_out)
+    check(_lib.load().mg_conv_seg_tc(C.byref(a), _stream()), "mg_conv_seg_tc")
+    if out16 is not None:
+        return out, hi, lo
+    return out
+
+
+def seg_tc_enabled():
+    """MG_SEG_TC=0 falls back to the direct fp32 kernel (thin_conv) for SPADE's mlp_shared."""
+    return os.environ.get("MG_SEG_TC", "1") != "0"
+
+
+def pack_mlp_shared(w_oihw):
+    """Operand of SPADE's mlp_shared conv (label_nc <= 4 -> 128, 3x3): tensor-core bf16 split, or the thin-conv layout."""
+    if seg_tc_enabled() and w_oihw.shape[0] == 128 and w_oihw.shape[1] <= 4:
+        return pack_weight_seg_tc(w_oihw)
+    return pack_weight_thin(w_oihw, 4)
+
+
+def mlp_shared(seg4, wpack, bias, *, seg_resize, out_hw, act=ACT_RELU, round_out=False, out16=None, want_f32=True):
+    """actv = act(conv3x3(nearest_resize(seg4)) + b) (normalization.py:110-111), dispatching on the packed operand."""
+    if wpack.dtype == torch.bfloat16:
+        return conv_seg_tc(seg4, wpack, bias, seg_resize=seg_resize, act=act, round_out=round_out, out_hw=out_hw, out16=out16,
+                           want_f32=want_f32)
+    return conv_thin(seg4, wpack, bias, 128, 3, 3, 1, 1, seg_resize=seg_resize, act=act, round_out=round_out, out_hw=out_hw,
+                     out16=out16, want_f32=want_f32)
 
 
 def conv_img(x, w_oihw, bias, act_in=ACT_LRELU, act_out=ACT_TANH):

@@ -368,6 +368,41 @@ def group_halo(pw="16", bo="1"):
     os.environ["MG_HALO"] = "1"
 
 
+def group_segtc():
+    """SPADE mlp_shared on tensor cores (bf16 hi/lo split concatenated along K) vs fp32 conv and vs the direct kernel."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (N, H, W, R, cin) in ((2, 32, 32, 1, 4), (1, 64, 64, 4, 4), (3, 16, 16, 2, 4), (2, 24, 40, 1, 3), (2, 128, 128, 2, 4)):
+        seg = torch.randn(N, 4, H * R, W * R, generator=g).to(dev)
+        if cin < 4:
+            seg[:, cin:] = 0
+        w = (torch.randn(128, cin, 3, 3, generator=g) / 6).to(dev)
+        b = torch.randn(128, generator=g).to(dev)
+        segr = seg[:, :cin, ::R, ::R].contiguous()
+        ref = F.relu(F.conv2d(segr, w, b, padding=1))
+        wp = ops.pack_weight_seg_tc(w)
+        got = ops.conv_seg_tc(nhwc(seg), wp, b, seg_resize=R if R > 1 else 0, out_hw=(H, W))
+        torch.cuda.synchronize()
+        report("seg_tc N%d %dx%d R%d cin%d fp32 out" % (N, H, W, R, cin), nchw(got), ref, 3e-5)
+        o32, hi, lo = ops.conv_seg_tc(nhwc(seg), wp, b, seg_resize=R if R > 1 else 0, out_hw=(H, W), out16=(ops.F16, False))
+        report("   fp16 copy", hi.float(), o32.half().float(), 0)
+        _, hi, lo = ops.conv_seg_tc(nhwc(seg), wp, b, seg_resize=R if R > 1 else 0, out_hw=(H, W), out16=(ops.BF16, True), want_f32=False)
+        report("   bf16 hi+lo", nchw(hi.float() + lo.float()), ref, 5e-5)
+        got = ops.conv_seg_tc(nhwc(seg), wp, b, seg_resize=R if R > 1 else 0, out_hw=(H, W), round_out=True)
+        report("   tf32-rounded out", nchw(got), ref, 6e-4)
+    seg = torch.randn(8, 512, 512, 4, device=dev)
+    w = torch.randn(128, 4, 3, 3, device=dev) / 6
+    b = torch.randn(128, device=dev)
+    wp, wt = ops.pack_weight_seg_tc(w), ops.pack_weight_thin(w, 4)
+    for label, kw in (("fp16 out", dict(out16=(ops.F16, False), want_f32=False)), ("fp32 out", dict(round_out=True))):
+        t1 = _time(lambda: ops.conv_seg_tc(seg, wp, b, **kw))
+        t0 = _time(lambda: ops.conv_thin(seg, wt, b, 128, 3, 3, 1, 1, act=1, **kw))
+        print("perf mlp_shared 8x512x512 %s: tensor-core %.3f ms, direct fp32 %.3f ms" % (label, t1, t0), flush=True)
+    segf = torch.randn(8, 512, 512, 4, device=dev)
+    t1 = _time(lambda: ops.conv_seg_tc(segf, wp, b, seg_resize=2, out_hw=(256, 256), out16=(ops.F16, False), want_f32=False))
+    t0 = _time(lambda: ops.conv_thin(segf, wt, b, 128, 3, 3, 1, 1, act=1, seg_resize=2, out_hw=(256, 256), out16=(ops.F16, False), want_f32=False))
+    print("perf mlp_shared 8x256x256 (R=2) fp16: tensor-core %.3f ms, direct fp32 %.3f ms" % (t1, t0), flush=True)
+
+
 def group_bwd():
     """tcgen05 weight gradient (MN-major operands, split-K) and data gradient (transposed conv)."""
     g = torch.Generator(device="cpu").manual_seed(31)
