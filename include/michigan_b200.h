@@ -143,6 +143,8 @@ int mg_pack_weight_thin(const float* w_oihw, float* wt, int O, int I, int CinP, 
  * Cout 128; a->w is the bf16 [128][128] operand written by mg_pack_weight_seg_tc. */
 int mg_conv_seg_tc(const mg_thin_args* a, void* stream);
 int mg_pack_weight_seg_tc(const float* w_oihw, void* wpack_bf16, int O, int I, void* stream);
+/* debugging aid: clock64() totals of CTA 0 of mg_conv_seg_tc under env MG_DBG=16 */
+int mg_debug_seg_prof(unsigned long long* host16);
 
 /* conv_img: tanh(conv3x3(lrelu(x))) 64->3, NHWC in, NCHW out (generator.py:227-228). */
 int mg_conv_img(const float* x, const float* w_oihw, const float* bias, float* out_nchw, int N, int H, int W,

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mg_pack_weight_thin": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_conv_seg_tc": [C.POINTER(ThinArgs), _p],
     "mg_pack_weight_seg_tc": [_p, _p, _i, _i, _p],
+    "mg_debug_seg_prof": [C.c_void_p],
     "mg_conv_img": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_to1": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_bn_stats": [_p, _ll, _i, _p, _p],

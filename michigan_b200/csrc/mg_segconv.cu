@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -21,6 +22,9 @@ namespace mg {
 constexpr int kSegThreads = 32 * 13;
 constexpr int kSegTileBytes = 2 * 16384;   // [128 rows x 128 K] bf16 as two K64 chunks of [128 x 128 B]
 
+// MG_DBG & 16: clock64() totals of CTA 0 (read back with mg_debug_seg_prof)
+__device__ unsigned long long g_seg_prof[16];
+
 struct SegParams {
     const float* seg;     // [N, IH*R, IW*R, 4]
     const float* bias;    // [128]
@@ -31,6 +35,7 @@ struct SegParams {
     int N, OH, OW, R;
     int tiles_w, tiles_h, num_tiles;
     uint32_t idesc;
+    int prof, dbg;   // dbg (MG_DBG bits, timing only): 1 no global stores, 2 no smem transposition
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -80,11 +85,16 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             tma_load_2d(w_s + 16384, &tmW, w_full, 64, 0);
             mbar_wait(w_full, 0);
             int it = 0;
+            const bool prof = p.prof && blockIdx.x == 0;
+            long long w_te = 0, w_af = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int s = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                long long t0 = prof ? clock64() : 0;
                 mbar_wait(&t_empty[s], ph ^ 1);
+                if (prof) { const long long t1 = clock64(); w_te += t1 - t0; t0 = t1; }
                 mbar_wait(&a_full[s], ph);
+                if (prof) w_af += clock64() - t0;
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(a_s + (size_t)s * kSegTileBytes), w_addr = smem_u32(w_s);
 #pragma unroll
@@ -97,6 +107,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
                 umma_commit(&a_empty[s]);
                 umma_commit(&t_full[s]);
             }
+            if (prof) { g_seg_prof[0] = (unsigned long long)(clock64() - t_begin); g_seg_prof[1] = (unsigned long long)w_te; g_seg_prof[2] = (unsigned long long)w_af; }
         }
     } else if (warp <= 4) {
         // ===================== operand builders: thread = pixel row of the tile =====================
@@ -105,11 +116,14 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
         const int IH = p.OH, IW = p.OW;
         const size_t row_stride = (size_t)IW * p.R * 4, img_stride = (size_t)IH * p.R * row_stride;
         int it = 0;
+        const bool prof = p.prof && blockIdx.x == 0 && r == 0;
+        long long c_gather = 0, c_wait = 0, c_store = 0, t_begin = prof ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             const int n = tile / tiles_per_img, m = tile - n * tiles_per_img;
             const int oh = (m / p.tiles_w) * 8 + th_l, ow = (m % p.tiles_w) * 16 + tw_l;
+            long long t0 = prof ? clock64() : 0;
             // gather the 3x3 neighbourhood (zero padding at the conv's resolution; nearest resize = index * R)
             uint2 hi[9], lo[9];
 #pragma unroll
@@ -123,7 +137,9 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
                 hi[t] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
                 lo[t] = make_uint2(pack_bf16x2(v.x - f01.x, v.y - f01.y), pack_bf16x2(v.z - f23.x, v.w - f23.y));
             }
+            if (prof) { const long long t1 = clock64(); c_gather += t1 - t0; t0 = t1; }
             mbar_wait(&a_empty[s], ph ^ 1);
+            if (prof) { const long long t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
             uint8_t* base = a_s + (size_t)s * kSegTileBytes + (size_t)r * 128;
             // K order: 8-byte groups g = 0..31: hi taps 0..8 | lo taps 0..8 | hi taps 0..8 | zeros
             auto group = [&](int g) -> uint2 {
@@ -140,20 +156,29 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
+            if (prof) c_store += clock64() - t0;
+        }
+        if (prof) {
+            g_seg_prof[3] = (unsigned long long)(clock64() - t_begin); g_seg_prof[4] = (unsigned long long)c_gather;
+            g_seg_prof[5] = (unsigned long long)c_wait; g_seg_prof[6] = (unsigned long long)c_store;
         }
     } else {
         // ===================== epilogue: 8 warps, (TMEM lane quarter) x (64-column half) =====================
         const int ew = warp - 5;
         const int quarter = warp & 3, half = ew >> 2;
-        float* scr = scratch + ew * (32 * 36);
+        float* scr = scratch + ew * (32 * 68);
         const int q = lane & 7, psub = lane >> 3;   // 8 lanes per pixel (32 channels), 4 pixels per pass
         int it = 0;
+        const bool prof = p.prof && blockIdx.x == 0 && ew == 0 && lane == 0;
+        long long c_wait = 0, c_ld = 0, c_rest = 0, t_begin = prof ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             const int n = tile / tiles_per_img, m = tile - n * tiles_per_img;
             const int oh0 = (m / p.tiles_w) * 8, ow0 = (m % p.tiles_w) * 16;
+            long long t0 = prof ? clock64() : 0;
             mbar_wait(&t_full[s], ph);
+            if (prof) { const long long t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128 + half * 64);
             uint32_t v0[16], v1[16], v2[16], v3[16];
@@ -161,38 +186,51 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&t_empty[s]);            // accumulator is in registers: release it before the stores
+            if (prof) { const long long t1 = clock64(); c_ld += t1 - t0; t0 = t1; }
+            // All 64 columns of this warp go through the scratch at once so that every global store request is a full
+            // 128-byte line (the SM->L2 write path moves about one request per 11 cycles whatever its size: 32/64-byte
+            // pieces made this kernel store-bound).  8 lanes serve one pixel: with a 16-bit output each lane owns 8
+            // consecutive channels (16 B -> 128 B per pixel and request); with an fp32 output it owns channels
+            // q*4..q*4+3 and 32+q*4.. (two requests of 8 x 16 B = 128 B each).
+            {
+                float4* d = reinterpret_cast<float4*>(scr + lane * 68);
+                if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                float4* d = reinterpret_cast<float4*>(scr + lane * 36);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t* a = cb == 0 ? v0 : v2;
-                    const uint32_t* b = cb == 0 ? v1 : v3;
-                    d[i] = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]), __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
-                    d[4 + i] = make_float4(__uint_as_float(b[4 * i]), __uint_as_float(b[4 * i + 1]), __uint_as_float(b[4 * i + 2]), __uint_as_float(b[4 * i + 3]));
+                    for (int i = 0; i < 4; ++i) {
+                        d[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]), __uint_as_float(v0[4 * i + 2]), __uint_as_float(v0[4 * i + 3]));
+                        d[4 + i] = make_float4(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]), __uint_as_float(v1[4 * i + 2]), __uint_as_float(v1[4 * i + 3]));
+                        d[8 + i] = make_float4(__uint_as_float(v2[4 * i]), __uint_as_float(v2[4 * i + 1]), __uint_as_float(v2[4 * i + 2]), __uint_as_float(v2[4 * i + 3]));
+                        d[12 + i] = make_float4(__uint_as_float(v3[4 * i]), __uint_as_float(v3[4 * i + 1]), __uint_as_float(v3[4 * i + 2]), __uint_as_float(v3[4 * i + 3]));
+                    }
                 }
                 __syncwarp();
-                const int ch = half * 64 + cb * 32 + q * 4;
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                const bool split = p.out != nullptr;                    // fp32 output present -> 4 + 4 channel ownership
+                const int c0 = split ? q * 4 : q * 8, c1 = split ? 32 + q * 4 : q * 8 + 4;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + half * 64 + c0));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + half * 64 + c1));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int r = quarter * 32 + j * 4 + psub;
                     const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
-                    const float4 t = *reinterpret_cast<const float4*>(scr + (j * 4 + psub) * 36 + q * 4);
-                    if (oh >= p.OH || ow >= p.OW) continue;
-                    float y[4] = {t.x + b4.x, t.y + b4.y, t.z + b4.z, t.w + b4.w};
+                    const float4 t0v = *reinterpret_cast<const float4*>(scr + (j * 4 + psub) * 68 + c0);
+                    const float4 t1v = *reinterpret_cast<const float4*>(scr + (j * 4 + psub) * 68 + c1);
+                    if (oh >= p.OH || ow >= p.OW || ((p.dbg & 1) && t0v.x != 12345.f)) continue;
+                    float y[8] = {t0v.x + b0.x, t0v.y + b0.y, t0v.z + b0.z, t0v.w + b0.w, t1v.x + b1.x, t1v.y + b1.y, t1v.z + b1.z, t1v.w + b1.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         if (p.act == 1) y[i] = fmaxf(y[i], 0.f);
                         else if (p.act == 2) y[i] = y[i] > 0.f ? y[i] : 0.2f * y[i];
                         if (p.round_out) y[i] = round_tf32(y[i]);
                     }
-                    const size_t eo = (((size_t)n * p.OH + oh) * p.OW + ow) * 128 + ch;
-                    if (p.out) *reinterpret_cast<float4*>(p.out + eo) = make_float4(y[0], y[1], y[2], y[3]);
+                    const size_t po = (((size_t)n * p.OH + oh) * p.OW + ow) * 128 + half * 64;
+                    if (p.out) {
+                        *reinterpret_cast<float4*>(p.out + po + c0) = make_float4(y[0], y[1], y[2], y[3]);
+                        *reinterpret_cast<float4*>(p.out + po + c1) = make_float4(y[4], y[5], y[6], y[7]);
+                    }
                     if (p.out_hi) {
-                        uint32_t h[2], l[2];
+                        uint32_t h[4], l[4];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
+                        for (int i = 0; i < 4; ++i) {
                             const float a = y[2 * i], b = y[2 * i + 1];
                             if (p.out16_fmt == 1) {
                                 const __half2 h2 = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
@@ -207,12 +245,28 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
                                 l[i] = pack_bf16x2(a - hf.x, b - hf.y);
                             }
                         }
-                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_hi) + eo) = make_uint2(h[0], h[1]);
-                        if (p.out_lo) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + eo) = make_uint2(l[0], l[1]);
+                        uint16_t* ph16 = reinterpret_cast<uint16_t*>(p.out_hi) + po;
+                        uint16_t* pl16 = p.out_lo ? reinterpret_cast<uint16_t*>(p.out_lo) + po : nullptr;
+                        if (!split) {
+                            *reinterpret_cast<uint4*>(ph16 + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+                            if (pl16) *reinterpret_cast<uint4*>(pl16 + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+                        } else {
+                            *reinterpret_cast<uint2*>(ph16 + c0) = make_uint2(h[0], h[1]);
+                            *reinterpret_cast<uint2*>(ph16 + c1) = make_uint2(h[2], h[3]);
+                            if (pl16) {
+                                *reinterpret_cast<uint2*>(pl16 + c0) = make_uint2(l[0], l[1]);
+                                *reinterpret_cast<uint2*>(pl16 + c1) = make_uint2(l[2], l[3]);
+                            }
+                        }
                     }
                 }
                 __syncwarp();
             }
+            if (prof) c_rest += clock64() - t0;
+        }
+        if (prof) {
+            g_seg_prof[7] = (unsigned long long)(clock64() - t_begin); g_seg_prof[8] = (unsigned long long)c_wait;
+            g_seg_prof[9] = (unsigned long long)c_ld; g_seg_prof[10] = (unsigned long long)c_rest;
         }
     }
     tc_fence_before();
@@ -239,6 +293,16 @@ __global__ void pack_weight_seg_tc_kernel(const float* __restrict__ w, __nv_bflo
 
 using namespace mg;
 
+// Debug: [0] MMA thread total, [1] wait accumulator-empty, [2] wait operand-full; [3] builder total, [4] gather, [5] wait
+// operand-empty, [6] store+fence; [7] epilogue warp 0 total, [8] wait accumulator-full, [9] TMEM load, [10] transpose+stores.
+extern "C" int mg_debug_seg_prof(unsigned long long* host16) {
+    if (!host16) return set_error(-1, "mg_debug_seg_prof: null pointer");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host16, g_seg_prof, 16 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return set_error((int)e, "mg_debug_seg_prof: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int mg_pack_weight_seg_tc(const float* w_oihw, void* wpack, int O, int I, void* stream_) {
     if (!w_oihw || !wpack) return set_error(-1, "mg_pack_weight_seg_tc: null pointer");
     if (O != 128 || I < 1 || I > 4) return set_error(-2, "mg_pack_weight_seg_tc: needs O = 128, I <= 4 (got %d, %d)", O, I);
@@ -262,6 +326,8 @@ extern "C" int mg_conv_seg_tc(const mg_thin_args* a, void* stream_) {
     p.N = a->N; p.OH = a->OH; p.OW = a->OW; p.R = a->seg_resize > 0 ? a->seg_resize : 1;
     p.tiles_w = (a->OW + 15) / 16; p.tiles_h = (a->OH + 7) / 8; p.num_tiles = p.tiles_w * p.tiles_h * a->N;
     p.idesc = umma_idesc_16(128, 128, 2);
+    p.prof = getenv("MG_DBG") ? (atoi(getenv("MG_DBG")) & 16) : 0;
+    p.dbg = getenv("MG_DBG") ? (atoi(getenv("MG_DBG")) & 3) : 0;
     CUtensorMap tmW;
     {
         cuuint64_t dims[2] = {128, 128};
@@ -271,7 +337,7 @@ extern "C" int mg_conv_seg_tc(const mg_thin_args* a, void* stream_) {
         int rc = encode_tensor_map(&tmW, (void*)a->w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    const size_t smem_bytes = 1024 + 3 * kSegTileBytes + 128 + 8 * 32 * 36 * 4;
+    const size_t smem_bytes = 1024 + 3 * kSegTileBytes + 128 + 8 * 32 * 68 * 4;
     static thread_local int attr_dev = -1;
     int dev = 0; cudaGetDevice(&dev);
     if (attr_dev != dev) {

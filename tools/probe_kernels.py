@@ -397,6 +397,17 @@ def group_segtc():
         t1 = _time(lambda: ops.conv_seg_tc(seg, wp, b, **kw))
         t0 = _time(lambda: ops.conv_thin(seg, wt, b, 128, 3, 3, 1, 1, act=1, **kw))
         print("perf mlp_shared 8x512x512 %s: tensor-core %.3f ms, direct fp32 %.3f ms" % (label, t1, t0), flush=True)
+    import ctypes
+    from michigan_b200 import _lib
+    names = ["mma total", "mma wait-acc-empty", "mma wait-operand", "builder total", "builder gather", "builder wait-empty", "builder store+fence",
+             "epi total", "epi wait-acc-full", "epi tmem-ld", "epi transpose+stores"]
+    for dbg in (16, 17, 18, 19):
+        os.environ["MG_DBG"] = str(dbg)
+        ops.conv_seg_tc(seg, wp, b, out16=(ops.F16, False), want_f32=False)
+        buf = (ctypes.c_ulonglong * 16)()
+        _lib.check(_lib.load().mg_debug_seg_prof(buf), "prof")
+        print("seg_tc MG_DBG=%d cycles (CTA 0, 111 tiles): " % dbg + ", ".join("%s %d" % (n, buf[i]) for i, n in enumerate(names)), flush=True)
+    os.environ["MG_DBG"] = "0"
     segf = torch.randn(8, 512, 512, 4, device=dev)
     t1 = _time(lambda: ops.conv_seg_tc(segf, wp, b, seg_resize=2, out_hw=(256, 256), out16=(ops.F16, False), want_f32=False))
     t0 = _time(lambda: ops.conv_thin(segf, wt, b, 128, 3, 3, 1, 1, act=1, seg_resize=2, out_hw=(256, 256), out16=(ops.F16, False), want_f32=False))
