@@ -154,9 +154,9 @@ def run_reference_arm(a):
 
 # ------------------------------------------------------------------------------------------ native arm
 # DRAM traffic of one launch of the dominant kernel from the `ncu --set full` capture committed as
-# profiles/r01_ncu_spade_gemm_f16_epilogue_v2.txt (dram__bytes_read.sum 809.4 MB + dram__bytes_write.sum 1027.4 MB at N=8);
+# profiles/r01_ncu_spade_gemm_f16_final.txt (dram__bytes_read.sum 817.4 MB + dram__bytes_write.sum 1028.9 MB at N=8);
 # algorithmic bytes = actv fp16 268 MB + x fp32 268 MB + weights 0.6 MB read, bf16 hi+lo 537 MB written.
-NCU_TRAFFIC_BYTES_N8 = 809.367296e6 + 1027.384e6
+NCU_TRAFFIC_BYTES_N8 = 817.437696e6 + 1028.886e6
 
 
 def dominant_kernel_roofline(batch):
@@ -300,11 +300,11 @@ def run_native(a):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "igemm_tf32_kernel<1> (fused SPADE gamma|beta implicit GEMM + modulate + LeakyReLU, up_3.norm_0 shape, "
+            "roofline": {"kernel": "igemm_tf32_kernel<1,16> (fused SPADE gamma|beta implicit GEMM + modulate + LeakyReLU, up_3.norm_0 shape, "
                                    "tcgen05 %s)" % kkind,
                          "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                          "traffic": NCU_TRAFFIC_BYTES_N8 * batch / 8 if kkind == "kind::f16" else None,
-                         "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01_ncu_spade_gemm_f16_*.txt)",
+                         "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01_ncu_spade_gemm_f16_final.txt)",
                          "peak_kind": "%s bf16 dense burst (MEASURED_PEAKS.json)%s" % (
                              pk_kind, "; kind::tf32 issues at half the bf16 rate" if kkind == "kind::tf32" else ""),
                          "ms_per_launch": kms, "flops_per_launch": kflops},

@@ -8,6 +8,7 @@
 //   IN:  same per (n,c) with g = dy*act'(xhat)
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cmath>
 #include "mg_internal.h"
 
@@ -336,6 +337,88 @@ thin_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, flo
     }
     if (part < parts)
         for (int k = k0; k < k1; ++k) atomicAdd(dwt + (size_t)k * Cout + co, acc[k - k0]);
+}
+
+// Register-tiled weight gradient of a thin conv (replaces the tensor-core route for Cin <= 8: with N = 32 padded channels
+// every tcgen05.mma sits on its ~100-cycle issue floor, profiles/r01_mma_rate_microbench.log).  Thread = (group of 4 output
+// channels) x (KPT of the KH*KW*CinP weight columns): per pixel one float4 of dz and KPT input values from shared memory
+// feed 4*KPT FMAs; the per-CTA partial sums stay in registers across all its tiles and are added atomically at the end.
+template <int KPT>
+__global__ void __launch_bounds__(256)
+thin_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ dwt, int N, int H, int W,
+                   int CinP, int OH, int OW, int Cout, int KH, int KW, int s, int pad, int pad_mode, int R, int tiles_w,
+                   int tiles_h, int num_tiles) {
+    extern __shared__ __align__(16) float sm[];
+    const int PH = 7 * s + KH, PW = 15 * s + KW;
+    float* in_s = sm;                                 // [PH][PW][CinP]
+    float* dz_s = sm + ((PH * PW * CinP + 3) & ~3);    // [128][Cout]
+    const int K = KH * KW * CinP;
+    const int G = Cout >> 2;                          // channel groups (16 or 32)
+    const int g = threadIdx.x % G, cg = threadIdx.x / G;
+    int xoff[KPT];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        const int k = cg * KPT + i;
+        const int kk = k < K ? k : 0;
+        const int ci = kk % CinP, tap = kk / CinP, kh = tap / KW, kw = tap - kh * KW;
+        xoff[i] = (kh * PW + kw) * CinP + ci;
+    }
+    float acc[KPT][4];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int n = tile / (tiles_w * tiles_h);
+        const int oh0 = th * 8, ow0 = tw * 16;
+        const int ih0 = oh0 * s - pad, iw0 = ow0 * s - pad;
+        __syncthreads();
+        for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+            const int py = i / PW, px = i - py * PW;
+            int ih = ih0 + py, iw = iw0 + px;
+            if (pad_mode == 1) {
+                if (ih < 0) ih = -ih;
+                if (ih >= H) ih = 2 * H - 2 - ih;
+                if (iw < 0) iw = -iw;
+                if (iw >= W) iw = 2 * W - 2 - iw;
+            }
+            const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+            for (int c = 0; c < CinP; c += 4) {
+                float4 v = make_float4(0, 0, 0, 0);
+                if (ok) v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H * R + (size_t)ih * R) * ((size_t)W * R) + (size_t)iw * R) * CinP + c));
+                *reinterpret_cast<float4*>(in_s + (size_t)i * CinP + c) = v;
+            }
+        }
+        for (int i = threadIdx.x; i < 128 * G; i += blockDim.x) {
+            const int c4 = i % G, pp = i / G;
+            const int oh = oh0 + (pp >> 4), ow = ow0 + (pp & 15);
+            float4 v = make_float4(0, 0, 0, 0);
+            if (oh < OH && ow < OW) v = __ldg(reinterpret_cast<const float4*>(dz + (((size_t)n * OH + oh) * OW + ow) * Cout + c4 * 4));
+            *reinterpret_cast<float4*>(dz_s + (size_t)pp * Cout + c4 * 4) = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int pp = 0; pp < 128; ++pp) {
+            const float4 d = *reinterpret_cast<const float4*>(dz_s + pp * Cout + g * 4);
+            const float* xb = in_s + (((pp >> 4) * s) * PW + (pp & 15) * s) * CinP;
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) {
+                const float xv = xb[xoff[i]];
+                acc[i][0] = fmaf(xv, d.x, acc[i][0]);
+                acc[i][1] = fmaf(xv, d.y, acc[i][1]);
+                acc[i][2] = fmaf(xv, d.z, acc[i][2]);
+                acc[i][3] = fmaf(xv, d.w, acc[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        const int k = cg * KPT + i;
+        if (k < K) {
+            float* dst = dwt + (size_t)k * Cout + g * 4;
+            atomicAdd(dst, acc[i][0]); atomicAdd(dst + 1, acc[i][1]); atomicAdd(dst + 2, acc[i][2]); atomicAdd(dst + 3, acc[i][3]);
+        }
+    }
 }
 
 // data gradient of a thin conv restricted to input channels [c_lo, c_lo+3): dimg NCHW [N,3,H,W]
@@ -816,17 +899,40 @@ extern "C" int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N,
     if (!x || !dz || !dwt) return set_error(-1, "mg_thin_wgrad: null pointer");
     if (Cout > 256 || 256 % Cout != 0) return set_error(-2, "mg_thin_wgrad: Cout must divide 256");
     const int K = KH * KW * CinP, parts = 256 / Cout;
-    if ((K + parts - 1) / parts > 64) return set_error(-3, "mg_thin_wgrad: K %d too large for %d parts", K, parts);
     const int PH = 7 * stride + KH, PW = 15 * stride + KW;
+    const int tiles_w = cdivb(OW, 16), tiles_h = cdivb(OH, 8), num_tiles = tiles_w * tiles_h * N;
+    int grid = num_sms();
+    if (grid > num_tiles) grid = num_tiles;
+    const int R = seg_resize > 0 ? seg_resize : 1;
+    cudaMemsetAsync(dwt, 0, (size_t)K * Cout * 4, ST(stream));
+    // register-tiled kernel: Cout 64/128, columns per thread = ceil(K / (256 / (Cout/4)))
+    const int CG = Cout == 64 || Cout == 128 ? 256 / (Cout / 4) : 0;
+    const int kpt = CG ? (K + CG - 1) / CG : 0;
+    static const bool legacy = getenv("MG_THIN_WGRAD_LEGACY") && atoi(getenv("MG_THIN_WGRAD_LEGACY")) != 0;
+    if (CG && kpt <= 13 && CinP % 4 == 0 && !legacy) {
+        const size_t smem = ((((size_t)PH * PW * CinP + 3) & ~(size_t)3) + 128 * (size_t)Cout) * 4;
+#define MG_TW2(KP)                                                                                                              \
+    do {                                                                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(thin_wgrad2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
+        if (e != cudaSuccess) return set_error((int)e, "thin_wgrad2 attr: %s", cudaGetErrorString(e));                           \
+        thin_wgrad2_kernel<KP><<<grid, 256, smem, ST(stream)>>>(x, dz, dwt, N, H, W, CinP, OH, OW, Cout, KH, KW, stride, pad,    \
+                                                                pad_mode, R, tiles_w, tiles_h, num_tiles);                        \
+    } while (0)
+        if (kpt <= 3) MG_TW2(3);
+        else if (kpt <= 5) MG_TW2(5);
+        else if (kpt <= 8) MG_TW2(8);
+        else MG_TW2(13);
+#undef MG_TW2
+        return check_launch("mg_thin_wgrad");
+    }
+    if ((K + parts - 1) / parts > 64) return set_error(-3, "mg_thin_wgrad: K %d too large for %d parts", K, parts);
     const size_t smem = ((size_t)PH * PW * CinP + 128 * (size_t)Cout) * 4;
     cudaError_t e = cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return set_error((int)e, "thin_wgrad attr: %s", cudaGetErrorString(e));
-    const int tiles_w = cdivb(OW, 16), tiles_h = cdivb(OH, 8), num_tiles = tiles_w * tiles_h * N;
-    int grid = num_sms() * 2;
-    if (grid > num_tiles) grid = num_tiles;
-    cudaMemsetAsync(dwt, 0, (size_t)K * Cout * 4, ST(stream));
-    thin_wgrad_kernel<<<grid, 256, smem, ST(stream)>>>(x, dz, dwt, N, H, W, CinP, OH, OW, Cout, KH, KW, stride, pad, pad_mode,
-                                                       seg_resize > 0 ? seg_resize : 1, tiles_w, tiles_h, num_tiles);
+    int grid2 = num_sms() * 2;
+    if (grid2 > num_tiles) grid2 = num_tiles;
+    thin_wgrad_kernel<<<grid2, 256, smem, ST(stream)>>>(x, dz, dwt, N, H, W, CinP, OH, OW, Cout, KH, KW, stride, pad, pad_mode, R,
+                                                        tiles_w, tiles_h, num_tiles);
     return check_launch("mg_thin_wgrad");
 }
 extern "C" int mg_thin_dgrad3(const float* dz, const float* wt, float* dimg_nchw, int N, int H, int W, int CinP, int OH, int OW, int Cout,

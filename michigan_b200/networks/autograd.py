@@ -118,13 +118,16 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     del dgb
     da = ops.act_bwd(dactv, actv, _RELU)
     del dactv, actv
-    seg32 = seg_cache.get(S.R) if seg_cache is not None else None
-    if seg32 is None:
-        seg32 = ops.pad_channels32(seg4, seg_resize=S.R, in_hw=S.hw)
-        if seg_cache is not None:
-            seg_cache.clear()          # one resolution at a time is alive (blocks run coarse -> fine in reverse)
-            seg_cache[S.R] = seg32
-    dwt = ops.thin_wgrad_tc(seg32, da, 3, 3, 1, 1, 4)
+    if ops.thin_wgrad_tc_enabled():
+        seg32 = seg_cache.get(S.R) if seg_cache is not None else None
+        if seg32 is None:
+            seg32 = ops.pad_channels32(seg4, seg_resize=S.R, in_hw=S.hw)
+            if seg_cache is not None:
+                seg_cache.clear()          # one resolution at a time is alive (blocks run coarse -> fine in reverse)
+                seg_cache[S.R] = seg32
+        dwt = ops.thin_wgrad_tc(seg32, da, 3, 3, 1, 1, 4)
+    else:
+        dwt = ops.thin_wgrad(seg4, da, 3, 3, 1, 1, seg_resize=S.R, in_hw=S.hw)
     G.add(sp.mlp_shared[0].weight, _thin_wt_to_oihw(dwt, 3, 3, 4))
     G.add(sp.mlp_shared[0].bias, ops.chan_sum(da))
     return dxhat, allreduce_sums(sums)
@@ -218,7 +221,9 @@ def fc_bwd(G, fc, S, dout):
         dy = ops.in_bwd(da, L.y_in, L.ss, _LRELU, pmul=L.pm_in)
     dz = ops.act_bwd(dy, None, _NONE, pm1=S.l1.upd, pm2=S.l1.ratio)
     G.add(fc.layer1.bias, ops.chan_sum(ops.act_bwd(dy, None, _NONE, pm1=S.l1.upd)))
-    G.add(fc.layer1.weight, _thin_wt_to_oihw(ops.thin_wgrad_tc(ops.pad_channels32(S.x0), dz, 3, 3, 2, 1, 4), 3, 3, 3))
+    dwt1 = (ops.thin_wgrad_tc(ops.pad_channels32(S.x0), dz, 3, 3, 2, 1, 4) if ops.thin_wgrad_tc_enabled()
+            else ops.thin_wgrad(S.x0, dz, 3, 3, 2, 1))
+    G.add(fc.layer1.weight, _thin_wt_to_oihw(dwt1, 3, 3, 3))
 
 
 def bg_fwd(bg, image, mask, noise):
@@ -254,7 +259,9 @@ def bg_bwd(G, bg, S, dfeats):
         d = ops.reflect_pad_bwd(dxp, 1, dx=d_list[i])
     dz0 = ops.act_bwd(d, S.x0, _RELU)
     G.add(bg.conv1.conv.bias, ops.chan_sum(dz0))
-    G.add(bg.conv1.conv.weight, _thin_wt_to_oihw(ops.thin_wgrad_tc(ops.pad_channels32(S.inp, reflect_pad=3), dz0, 7, 7, 1, 0, 4), 7, 7, 3))
+    dwt1 = (ops.thin_wgrad_tc(ops.pad_channels32(S.inp, reflect_pad=3), dz0, 7, 7, 1, 0, 4) if ops.thin_wgrad_tc_enabled()
+            else ops.thin_wgrad(S.inp, dz0, 7, 7, 1, 3, pad_mode=1))
+    G.add(bg.conv1.conv.weight, _thin_wt_to_oihw(dwt1, 7, 7, 3))
 
 
 # =============================================================================================== generator Function
@@ -356,7 +363,9 @@ def _d_scale_bwd(G, D, S, douts, inv_of, need_dimg, param_grads):
     conv0 = D.model0[0]
     dz0 = ops.act_bwd(df, S.f0, _LRELU)
     if param_grads:
-        G.add(conv0.weight, _thin_wt_to_oihw(ops.thin_wgrad_tc(ops.pad_channels32(S.x8), dz0, 4, 4, 2, D.padw, 8), 4, 4, conv0.weight.shape[1]))
+        dwt0 = (ops.thin_wgrad_tc(ops.pad_channels32(S.x8), dz0, 4, 4, 2, D.padw, 8) if ops.thin_wgrad_tc_enabled()
+                else ops.thin_wgrad(S.x8, dz0, 4, 4, 2, D.padw))
+        G.add(conv0.weight, _thin_wt_to_oihw(dwt0, 4, 4, conv0.weight.shape[1]))
         G.add(conv0.bias, ops.chan_sum(dz0))
     if not need_dimg:
         return None

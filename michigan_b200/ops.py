@@ -578,6 +578,12 @@ def pad_channels32(x, seg_resize=0, in_hw=None, reflect_pad=0):
     return out
 
 
+def thin_wgrad_tc_enabled():
+    """MG_THIN_WGRAD_TC=1 routes the thin-conv weight gradients through the tensor-core wgrad on 32-padded channels
+    (N = 32 MMAs sit on the ~100-cycle issue floor); default is the register-tiled CUDA-core kernel (mg_thin_wgrad)."""
+    return os.environ.get("MG_THIN_WGRAD_TC", "0") == "1"
+
+
 def thin_wgrad_tc(x32, dz, kh, kw, stride, pad, cinp):
     """Weight gradient of a thin conv on the tensor cores: x32 from pad_channels32 (already reflect-padded when the
     conv uses reflection padding: pass pad=0 then).  Returns the thin layout [kh*kw][cinp][Cout]."""
@@ -588,7 +594,7 @@ def thin_wgrad_tc(x32, dz, kh, kw, stride, pad, cinp):
 
 def thin_wgrad(x, dz, kh, kw, stride, pad, pad_mode=0, seg_resize=0, in_hw=None):
     """dwt [kh*kw][CinP][Cout] of a thin conv; x is the (possibly full-resolution seg) input.
-    (CUDA-core reference kernel; the training path uses thin_wgrad_tc.)"""
+    Register-tiled CUDA-core kernel (4 output channels x <= 13 weight columns per thread)."""
     _chk(x, "x"); _chk(dz, "dz")
     N, OH, OW, Cout = dz.shape
     CinP = x.shape[-1]

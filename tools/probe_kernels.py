@@ -508,6 +508,17 @@ def group_bwd2():
     report("thin_wgrad seg_resize", dwt.view(3, 3, 4, 128).permute(3, 2, 0, 1), w.grad, 2e-5)
     dwt2 = ops.thin_wgrad_tc(ops.pad_channels32(nhwc(seg), seg_resize=4, in_hw=(16, 16)), nhwc(dz), 3, 3, 1, 1, 4)
     report("thin_wgrad_tc seg_resize (tf32)", dwt2.view(3, 3, 4, 128).permute(3, 2, 0, 1), w.grad, 2e-3)
+    # timing at the training shapes: register-tiled CUDA-core kernel vs the tensor-core route on 32-padded channels
+    for label, cinp, cout, k, s_, p_, pm, S_, Nn in (("bg conv1 3->64 k7 reflect 8x512^2", 4, 64, 7, 1, 3, 1, 512, 8),
+                                                    ("D model0 7->64 k4 s2 16x512^2", 8, 64, 4, 2, 2, 0, 512, 16),
+                                                    ("mlp_shared 4->128 k3 8x512^2", 4, 128, 3, 1, 1, 0, 512, 8)):
+        xin = torch.randn(Nn, S_, S_, cinp, device=dev)
+        oh = (S_ + 2 * p_ - k) // s_ + 1
+        dzz = torch.randn(Nn, oh, oh, cout, device=dev)
+        t_new = _time(lambda: ops.thin_wgrad(xin, dzz, k, k, s_, p_, pad_mode=pm))
+        t_tc = _time(lambda: ops.thin_wgrad_tc(ops.pad_channels32(xin, reflect_pad=p_) if pm else ops.pad_channels32(xin), dzz, k, k, s_, 0 if pm else p_, cinp))
+        print("perf thin wgrad %-36s register-tiled %.3f ms, tensor-core(32-padded, incl. pad) %.3f ms" % (label, t_new, t_tc), flush=True)
+        del xin, dzz
     # ---- conv_img backward
     x = torch.randn(2, 64, 24, 40, generator=g).to(dev).requires_grad_(True)
     w = (torch.randn(3, 64, 3, 3, generator=g) / 24).to(dev).requires_grad_(True)
