@@ -911,6 +911,12 @@ extern "C" int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N,
     static const bool legacy = getenv("MG_THIN_WGRAD_LEGACY") && atoi(getenv("MG_THIN_WGRAD_LEGACY")) != 0;
     if (CG && kpt <= 13 && CinP % 4 == 0 && !legacy) {
         const size_t smem = ((((size_t)PH * PW * CinP + 3) & ~(size_t)3) + 128 * (size_t)Cout) * 4;
+        // load -> sync -> compute per tile: co-resident CTAs overlap one's loads with another's FMAs
+        int per_sm = (int)((200 * 1024) / (smem + 1024));
+        if (per_sm > 3) per_sm = 3;
+        if (per_sm < 1) per_sm = 1;
+        grid = num_sms() * per_sm;
+        if (grid > num_tiles) grid = num_tiles;
 #define MG_TW2(KP)                                                                                                              \
     do {                                                                                                                         \
         cudaError_t e = cudaFuncSetAttribute(thin_wgrad2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
