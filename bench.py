@@ -256,19 +256,49 @@ def run_native(a):
             dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
         ms_total = ms_total.item()
 
-        # ---- end to end through the public API with host buffers
-        def e2e_step():
-            img = model(host, mode="inference")
-            host_out.copy_(img, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        # ---- end to end through the public API with host buffers.  Every step copies its inputs from pinned host memory
+        # and reads its result back into pinned host memory; like a prefetching data loader the copies run on a second
+        # stream (double-buffered), so step i+1's H2D and step i-1's D2H overlap step i's kernels.
+        copy_stream = torch.cuda.Stream()
+        main_stream = torch.cuda.current_stream()
+        host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+        tensor_keys = [k for k, v in host.items() if torch.is_tensor(v)]
 
-        for _ in range(max(1, a.warmup // 2 + 1)):
-            e2e_step()
+        # two device-side input sets allocated once (no allocator traffic on the copy stream)
+        dev_sets = [{k: torch.empty_like(host[k], device="cuda") for k in tensor_keys} for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                for k in tensor_keys:
+                    dev_sets[i & 1][k].copy_(host[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            dev = dict(host)
+            dev.update(dev_sets[i & 1])
+            return dev, ev
+
+        def e2e_run(nsteps):
+            nxt = prefetch(0)
+            for i in range(nsteps):
+                dev, ev = nxt
+                main_stream.wait_event(ev)
+                if i + 1 < nsteps:
+                    nxt = prefetch(i + 1)   # queued behind step i-1's read-back, which waited for step i-1's kernels
+                img = model(dev, mode="inference")
+                done = torch.cuda.Event()
+                done.record(main_stream)
+                img.record_stream(copy_stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    host_outs[i & 1].copy_(img, non_blocking=True)
+            copy_stream.synchronize()
+            main_stream.synchronize()
+
+        e2e_run(max(2, a.warmup // 2 + 1))
         barrier()
         e2e_steps = a.steps
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_run(e2e_steps)
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -297,7 +327,9 @@ def run_native(a):
                        "algorithmic_gflop_per_image": G_FWD_GFLOP_PER_IMG},
             "achieved_tflops_step": G_FWD_GFLOP_PER_IMG * batch / ms_step,
             "e2e": {"value": world * batch * e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h,
+                    "how": "Pix2PixModel(data, mode='inference') per step; pinned host inputs -> device and image -> pinned host every "
+                           "step, copies double-buffered on a second stream (prefetching-loader style), wall clock"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "igemm_tf32_kernel<1,16> (fused SPADE gamma|beta implicit GEMM + modulate + LeakyReLU, up_3.norm_0 shape, "
