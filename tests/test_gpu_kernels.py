@@ -1,0 +1,170 @@
+"""Kernel-level parity through the C ABI (ctypes -> libmichigan_sm100.so) against plain PyTorch fp32 references of
+the same op on the same seeded inputs.  Tolerances (relative to the reference's abs-max) are stated per case:
+operands pre-rounded to the kernel's input format are compared at fp32-accumulation accuracy (2e-5 .. 3e-5); the bf16
+hi/lo split paths are compared against the UNROUNDED fp32 conv at 6e-5 (~16 significand bits)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _ops():
+    from michigan_b200 import ops
+    return ops
+
+
+def tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-6)
+
+
+@pytest.fixture()
+def gen():
+    return torch.Generator(device="cpu").manual_seed(1234)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p", [
+    (2, 32, 32, 64, 64, 3, 1, 1), (1, 16, 16, 32, 32, 1, 1, 0), (3, 8, 8, 64, 64, 3, 1, 1), (5, 4, 4, 64, 32, 3, 1, 1),
+    (2, 33, 33, 64, 128, 4, 2, 2), (2, 65, 65, 64, 128, 4, 1, 2), (2, 64, 64, 64, 128, 3, 2, 1), (2, 24, 40, 128, 256, 3, 1, 1)])
+def test_igemm_tf32_vs_conv2d(gen, N, H, W, Cin, Cout, k, s, p):
+    """Implicit-GEMM conv (architecture.py:31-34, discriminator.py:84-96 geometries), TF32-exact operands: 2e-5."""
+    ops = _ops()
+    x = tf32_trunc(torch.randn(N, Cin, H, W, generator=gen).to(dev))
+    w = tf32_trunc((torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).to(dev))
+    b = torch.randn(Cout, generator=gen).to(dev)
+    ref = F.leaky_relu(F.conv2d(x, w, b, stride=s, padding=p), 0.2)
+    got = ops.conv_igemm(nhwc(x), ops.pack_weight(w, None, round_tf32=True), Cout, k, k, s, p, bias=b, act=ops.ACT_LRELU)
+    assert rel_err(nchw(got), ref) <= 2e-5
+
+
+@pytest.mark.parametrize("N,h,Cin,Cout,k,s,p", [(2, 32, 64, 64, 3, 1, 1), (2, 33, 128, 256, 4, 2, 2), (1, 64, 256, 128, 3, 1, 1),
+                                              (3, 8, 64, 64, 1, 1, 0)])
+def test_igemm_16bit_operands(gen, N, h, Cin, Cout, k, s, p):
+    """fp16 one pass (exact on fp16-rounded operands) and bf16 hi/lo split (merged 2-MMA form for N <= 128, 3 passes
+    otherwise; MG_MERGE=0 forces 3 passes) against the unrounded fp32 conv."""
+    ops = _ops()
+    x = torch.randn(N, Cin, h, h, generator=gen).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=gen).to(dev)
+    got = ops.conv_igemm(nhwc(x).half(), ops.pack_weight16(w, None, ops.F16, split=False), Cout, k, k, s, p, bias=b, a_fmt=ops.F16)
+    assert rel_err(nchw(got), F.conv2d(x.half().float(), w.half().float(), b, stride=s, padding=p)) <= 2e-5
+    xn = nhwc(x)
+    hi = xn.bfloat16()
+    lo = (xn - hi.float()).bfloat16()
+    ref32 = F.conv2d(x, w, b, stride=s, padding=p)
+    wp3 = ops.pack_weight16(w, None, ops.BF16, split=True)
+    for merge in ("1", "0"):
+        os.environ["MG_MERGE"] = merge
+        try:
+            got = ops.conv_igemm(hi, wp3, Cout, k, k, s, p, bias=b, a_fmt=ops.BF16, x_lo=lo)
+        finally:
+            os.environ.pop("MG_MERGE", None)
+        assert rel_err(nchw(got), ref32) <= 6e-5, merge
+
+
+def test_igemm_halo_mode_matches_classic(gen):
+    """MG_HALO=1 (one input patch per K chunk, taps through shifted UMMA descriptors) is an alternative schedule of the
+    same GEMM: results must agree with the classic per-tap loads to accumulation-order noise."""
+    ops = _ops()
+    x = tf32_trunc(torch.randn(2, 64, 24, 40, generator=gen).to(dev))
+    w = tf32_trunc((torch.randn(128, 64, 3, 3, generator=gen) / 24).to(dev))
+    wp = ops.pack_weight(w, None, round_tf32=True)
+    outs = []
+    for halo in ("0", "1"):
+        os.environ["MG_HALO"] = halo
+        try:
+            outs.append(ops.conv_igemm(nhwc(x), wp, 128, 3, 3, 1, 1))
+        finally:
+            os.environ.pop("MG_HALO", None)
+    ref = F.conv2d(x, w, None, padding=1)
+    assert rel_err(nchw(outs[0]), ref) <= 2e-5 and rel_err(nchw(outs[1]), ref) <= 2e-5
+    assert rel_err(outs[1], outs[0]) <= 2e-6
+
+
+@pytest.mark.parametrize("N,h,C,xs", [(2, 32, 64, 0), (2, 32, 128, 1), (1, 64, 32, 0), (3, 8, 256, 1)])
+def test_fused_spade_epilogue(gen, N, h, C, xs):
+    """normalization.py:110-116 + architecture.py:85 in one kernel: out = lrelu((x-mean)*rstd * (1+gamma) + beta) with
+    gamma|beta = conv3x3(actv) in the accumulator, x read at half resolution when the upsample is folded (xs = 1)."""
+    ops = _ops()
+    actv = tf32_trunc(torch.randn(N, 128, h, h, generator=gen).to(dev))
+    wg = tf32_trunc((torch.randn(C, 128, 3, 3, generator=gen) / 34.0).to(dev))
+    wb = tf32_trunc((torch.randn(C, 128, 3, 3, generator=gen) / 34.0).to(dev))
+    bg = torch.randn(C, generator=gen).to(dev) * 0.1
+    bb = torch.randn(C, generator=gen).to(dev) * 0.1
+    x = torch.randn(N, C, h >> xs, h >> xs, generator=gen).to(dev)
+    mean = torch.randn(C, generator=gen).to(dev) * 0.1
+    rstd = torch.rand(C, generator=gen).to(dev) + 0.5
+    gamma = F.conv2d(actv, wg, bg, padding=1)
+    beta = F.conv2d(actv, wb, bb, padding=1)
+    xu = F.interpolate(x, scale_factor=2 ** xs, mode="nearest") if xs else x
+    ref = F.leaky_relu((xu - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1) * (1 + gamma) + beta, 0.2)
+    got = ops.conv_igemm(nhwc(actv), ops.pack_weight_gb(wg, wb), C, 3, 3, 1, 1, act=ops.ACT_LRELU,
+                         spade=(nhwc(x), xs, rstd.contiguous(), (-mean * rstd).contiguous(), (1 + bg).contiguous(), bb))
+    assert rel_err(nchw(got), ref) <= 3e-5
+
+
+@pytest.mark.parametrize("N,H,W,R,cin", [(2, 32, 32, 1, 4), (1, 64, 64, 4, 4), (3, 16, 16, 2, 4), (2, 24, 40, 1, 3)])
+def test_seg_conv_tensor_core(gen, N, H, W, R, cin):
+    """SPADE mlp_shared (normalization.py:92-96,110-111) as one K=128 bf16-split GEMM vs fp32 conv: 3e-5; the direct
+    fp32 kernel (MG_SEG_TC=0 route) must agree as well."""
+    ops = _ops()
+    seg = torch.randn(N, 4, H * R, W * R, generator=gen).to(dev)
+    seg[:, cin:] = 0
+    w = (torch.randn(128, cin, 3, 3, generator=gen) / 6).to(dev)
+    b = torch.randn(128, generator=gen).to(dev)
+    ref = F.relu(F.conv2d(seg[:, :cin, ::R, ::R].contiguous(), w, b, padding=1))
+    got = ops.conv_seg_tc(nhwc(seg), ops.pack_weight_seg_tc(w), b, seg_resize=R if R > 1 else 0, out_hw=(H, W))
+    assert rel_err(nchw(got), ref) <= 3e-5
+    direct = ops.conv_thin(nhwc(seg), ops.pack_weight_thin(w, 4), b, 128, 3, 3, 1, 1, seg_resize=R if R > 1 else 0, act=ops.ACT_RELU,
+                           out_hw=(H, W))
+    assert rel_err(nchw(direct), ref) <= 2e-5
+    o32, hi, _ = ops.conv_seg_tc(nhwc(seg), ops.pack_weight_seg_tc(w), b, seg_resize=R if R > 1 else 0, out_hw=(H, W), out16=(ops.F16, False))
+    assert torch.equal(hi.float(), o32.half().float())
+
+
+@pytest.mark.parametrize("Cin,CinP,Cout,k,s,p,pm", [(4, 4, 128, 3, 1, 1, 0), (7, 8, 64, 4, 2, 2, 0), (3, 4, 64, 7, 1, 3, 1), (3, 4, 64, 3, 2, 1, 0)])
+def test_thin_wgrad_vs_autograd(gen, Cin, CinP, Cout, k, s, p, pm):
+    """Weight gradient of the thin convs (mlp_shared, D model0, bg conv1 with reflection padding, fc.layer1): fp32
+    register-tiled kernel vs torch autograd, 2e-5 relative (summation order)."""
+    ops = _ops()
+    x = torch.randn(2, Cin, 32, 32, generator=gen).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).to(dev).requires_grad_(True)
+    xin = F.pad(x, (p, p, p, p), mode="reflect") if pm else x
+    y = F.conv2d(xin, w, None, stride=s, padding=0 if pm else p)
+    dz = torch.randn(y.shape, generator=gen).to(dev)
+    y.backward(dz)
+    dwt = ops.thin_wgrad(ops.nchw_to_nhwc(x, CinP), nhwc(dz), k, k, s, p, pad_mode=pm)
+    dw = dwt.view(k, k, CinP, Cout)[:, :, :Cin].permute(3, 2, 0, 1)
+    assert rel_err(dw, w.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("N,h,Cin,Cout,k,s,p", [(2, 32, 64, 64, 3, 1, 1), (2, 33, 64, 128, 4, 2, 2), (3, 8, 128, 64, 1, 1, 0), (2, 32, 64, 128, 3, 2, 1)])
+def test_tensor_core_wgrad_and_dgrad(gen, N, h, Cin, Cout, k, s, p):
+    """wgrad (both operands MN-major from NHWC, one filter row per CTA) and dgrad (the forward kernel on dY with per-parity
+    flipped sub-filters) vs torch autograd on TF32-exact operands: 5e-5 (split-K atomics reorder the fp32 sums)."""
+    ops = _ops()
+    x = tf32_trunc(torch.randn(N, Cin, h, h, generator=gen).to(dev)).requires_grad_(True)
+    w = tf32_trunc((torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).to(dev)).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride=s, padding=p)
+    dy = tf32_trunc(torch.randn(y.shape, generator=gen).to(dev))
+    y.backward(dy)
+    dwp = ops.conv_wgrad(nhwc(dy), nhwc(x.detach()), k, k, s, p)
+    dw = ops.unpack_wgrad(dwp, tuple(w.shape))
+    assert rel_err(dw, w.grad) <= 5e-5
+    dx = ops.conv_dgrad(nhwc(dy), w.detach(), (h, h), s, p)
+    assert rel_err(nchw(dx), x.grad) <= 5e-5
