@@ -12,6 +12,16 @@ pytestmark = pytest.mark.gpu
 dev = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    """The PyTorch references must be true fp32: cuDNN/cuBLAS use TF32 for fp32 convs unless told otherwise."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _ops():
     from michigan_b200 import ops
     return ops
