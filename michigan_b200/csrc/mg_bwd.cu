@@ -586,8 +586,16 @@ conv_img_wgrad_kernel(const float* __restrict__ dz4, const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------ Cin -> 1 conv backward
-__global__ void conv_to1_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, float* __restrict__ dx, int N,
-                                      int H, int W, int Cin, int KH, int KW, int pad, int OH, int OW, int accumulate) {
+__global__ void __launch_bounds__(256)
+conv_to1_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, float* __restrict__ dx, int N,
+                      int H, int W, int Cin, int KH, int KW, int pad, int OH, int OW, int accumulate) {
+    // weights transposed to [tap][Cin] in shared memory: consecutive lanes (channel groups) read consecutive float4
+    extern __shared__ __align__(16) float w_s[];
+    for (int i = threadIdx.x; i < KH * KW * Cin; i += blockDim.x) {
+        const int c = i % Cin, tap = i / Cin;
+        w_s[i] = w[(size_t)c * KH * KW + tap];
+    }
+    __syncthreads();
     const int G = Cin / 4;
     const long long total = (long long)N * H * W * G;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -605,8 +613,8 @@ __global__ void conv_to1_dgrad_kernel(const float* __restrict__ dl, const float*
                 const int ow = iw + pad - kw;
                 if (ow < 0 || ow >= OW) continue;
                 const float d = __ldg(dl + ((size_t)n * OH + oh) * OW + ow);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = fmaf(d, __ldg(w + (size_t)(g0 * 4 + i) * KH * KW + kh * KW + kw), a[i]);
+                const float4 wv = *reinterpret_cast<const float4*>(w_s + (size_t)(kh * KW + kw) * Cin + g0 * 4);
+                a[0] = fmaf(d, wv.x, a[0]); a[1] = fmaf(d, wv.y, a[1]); a[2] = fmaf(d, wv.z, a[2]); a[3] = fmaf(d, wv.w, a[3]);
             }
         }
         float4 o = make_float4(a[0], a[1], a[2], a[3]);
@@ -974,7 +982,7 @@ extern "C" int mg_conv_to1_bwd(const float* dl, const float* x, const float* w, 
     if (!dl || !x || !w) return set_error(-1, "mg_conv_to1_bwd: null pointer");
     const int OH = H + 2 * pad - KH + 1, OW = W + 2 * pad - KW + 1;
     if (dx) {
-        conv_to1_dgrad_kernel<<<ew_grid_b((long long)N * H * W * (Cin / 4)), 256, 0, ST(stream)>>>(dl, w, dx, N, H, W, Cin, KH, KW, pad, OH, OW,
+        conv_to1_dgrad_kernel<<<ew_grid_b((long long)N * H * W * (Cin / 4)), 256, (size_t)KH * KW * Cin * 4, ST(stream)>>>(dl, w, dx, N, H, W, Cin, KH, KW, pad, OH, OW,
                                                                                                  accumulate_dx);
         count_launch();
     }
