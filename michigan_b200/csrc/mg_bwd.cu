@@ -543,15 +543,23 @@ conv_img_wgrad_kernel(const float* __restrict__ dz4, const float* __restrict__ x
         const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
         const int h0 = th * 8 - 1, w0 = tw * 32 - 1;
         __syncthreads();
-        for (int i = threadIdx.x; i < NP * Cin; i += blockDim.x) {
-            const int c = i % Cin, pp = i / Cin;
-            const int ih = h0 + pp / PW, iw = w0 + pp % PW;
-            float v = 0.f;
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                v = x[(((size_t)n * H + ih) * W + iw) * Cin + c];
-                v = act_in == MG_ACT_LRELU ? (v > 0.f ? v : 0.2f * v) : v;
+        {
+            // fill: thread = (pixel group, float4 channel group); one integer division per pixel instead of four per element
+            const int C4 = Cin >> 2, c4 = threadIdx.x % C4, pg = threadIdx.x / C4, npg = 256 / C4;
+            for (int pp = pg; pp < NP; pp += npg) {
+                const int py = pp / PW, px = pp - py * PW;
+                const int ih = h0 + py, iw = w0 + px;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                    v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * Cin) + c4);
+                    if (act_in == MG_ACT_LRELU) {
+                        v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+                        v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+                    }
+                }
+                float* d = in_s + (size_t)pp * (Cin + 1) + c4 * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             }
-            in_s[(size_t)pp * (Cin + 1) + c] = v;
         }
         {
             const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
@@ -573,10 +581,16 @@ conv_img_wgrad_kernel(const float* __restrict__ dz4, const float* __restrict__ x
                 }
             }
         }
-        if (threadIdx.x < 3) {
-            float s = 0.f;
-            for (int pp = 0; pp < 256; ++pp) s += dz_s[pp * 4 + threadIdx.x];
-            bacc[threadIdx.x] += s;
+        if (threadIdx.x < 32) {
+            // bias gradient: lane sums 8 pixels, butterfly over the warp; lanes 0..2 keep channels 0..2
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            for (int pp = threadIdx.x; pp < 256; pp += 32) { s0 += dz_s[pp * 4]; s1 += dz_s[pp * 4 + 1]; s2 += dz_s[pp * 4 + 2]; }
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (threadIdx.x == 0) bacc[0] += s0;
+            if (threadIdx.x == 1) bacc[1] += s1;
+            if (threadIdx.x == 2) bacc[2] += s2;
         }
     }
     if (tg < tgn)
