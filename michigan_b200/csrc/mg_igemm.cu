@@ -28,7 +28,9 @@
 namespace mg {
 
 constexpr int kNumEpiWarps = 8;
-constexpr int kThreads = 64 + kNumEpiWarps * 32;  // 320
+// warps 0/1: TMA producer + MMA issuer of pipeline 0, warps 2..9: epilogue, warps 10/11: producer + issuer of pipeline 1
+// (dual mode: the two pipelines work on alternate tiles / TMEM accumulators, see IgemmParams::dual)
+constexpr int kThreads = 64 + kNumEpiWarps * 32 + 64;  // 384
 constexpr int kABytes = 128 * 128;                // 128 pixels x 32 fp32
 constexpr int kMaxStages = 8;
 constexpr int kMaxASlots = 4;
@@ -69,6 +71,10 @@ struct IgemmParams {
     // halo mode (3x3, stride 1, pad 1): one [PW x (TH+2)] input patch per K chunk serves all 9 taps
     int halo, PW, patch_bytes, patch_tx, a_slots, b_slots, b_slot_bytes, acc_cols, merged, n_items, bo_mode, bar_off;
     uint32_t idesc2;
+    // dual mode: a single thread issues at most one tcgen05.mma per ~100-120 cycles whatever its N (microbenchmark
+    // profiles/r01_mma_rate_two_issuers.log: N=64 120 -> 62 cycles/MMA with two issuers, N=128 120 -> 85), so thin-N layers
+    // run two independent (producer, issuer) pairs, each with half of the stage ring and one of the two accumulators.
+    int dual, ring_stages;
     int dbg;   // what-if probes (env MG_DBG; 1..8 give WRONG results): 1 no B loads after the first tile, 2 no A loads, 4 no epilogue work, 8 no epilogue global traffic (32 no 16-bit stores only, 64 no x loads only), 16 cycle profile
 };
 
@@ -270,14 +276,18 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 g_igemm_prof[3] = (unsigned long long)w_tempty; g_igemm_prof[4] = (unsigned long long)w_full;
             }
         }
-    } else if (warp == 0) {
-        // ===================== TMA producer (one thread) =====================
+    } else if (warp == 0 || (p.dual && warp == 10)) {
+        // ===================== TMA producer (one thread per pipeline) =====================
         if (lane == 0) {
+            const int pipe = warp == 10 ? 1 : 0, npipes = p.dual ? 2 : 1;
+            uint64_t* const full_bar_p = full_bar + pipe * p.ring_stages;
+            uint64_t* const empty_bar_p = empty_bar + pipe * p.ring_stages;
+            uint8_t* const ring = smem + (size_t)pipe * p.ring_stages * stage_bytes;
             int st = 0;
             uint32_t ph = 0;
-            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            const bool prof = (p.dbg & 16) && blockIdx.x == 0 && pipe == 0;
             long long w_empty = 0, t_begin = prof ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += npipes * gridDim.x) {
                 const bool ldA = !(p.dbg & 2) || tile == (int)blockIdx.x, ldB = !(p.dbg & 1) || tile == (int)blockIdx.x;
                 const int nt = tile % p.n_tiles;
                 const int m = tile / p.n_tiles;
@@ -298,35 +308,39 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const bool both = p.merged && part == 0;
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             const long long t0 = prof ? clock64() : 0;
-                            mbar_wait(&empty_bar[st], ph ^ 1);
+                            mbar_wait(&empty_bar_p[st], ph ^ 1);
                             if (prof) w_empty += clock64() - t0;
-                            uint8_t* sa = smem + (size_t)st * stage_bytes;
+                            uint8_t* sa = ring + (size_t)st * stage_bytes;
                             const uint32_t txs = (ldA ? kABytes : 0) + (ldB ? p.BN * 128 * (both ? 2 : 1) : 0);
-                            if (txs == 0) { mbar_arrive(&full_bar[st]); }
-                            else mbar_arrive_expect_tx(&full_bar[st], txs);
-                            if (ldA) tma_load_4d(sa, ta, &full_bar[st], kc * p.kelem, iw0 + kw, ih0 + kh, n0);
+                            if (txs == 0) { mbar_arrive(&full_bar_p[st]); }
+                            else mbar_arrive_expect_tx(&full_bar_p[st], txs);
+                            if (ldA) tma_load_4d(sa, ta, &full_bar_p[st], kc * p.kelem, iw0 + kw, ih0 + kh, n0);
                             const int kofs = (tap * bparts + bsel) * p.Cin + kc * p.kelem;
                             if (ldB) {
-                                tma_load_2d(sa + kABytes, &tmB, &full_bar[st], kofs, nt * p.BN);
-                                if (both) tma_load_2d(sa + kABytes + p.BN * 128, &tmB, &full_bar[st], kofs + p.Cin, nt * p.BN);
+                                tma_load_2d(sa + kABytes, &tmB, &full_bar_p[st], kofs, nt * p.BN);
+                                if (both) tma_load_2d(sa + kABytes + p.BN * 128, &tmB, &full_bar_p[st], kofs + p.Cin, nt * p.BN);
                             }
-                            if (++st == p.stages) { st = 0; ph ^= 1; }
+                            if (++st == p.ring_stages) { st = 0; ph ^= 1; }
                         }
                     }
                 }
             }
             if (prof) { g_igemm_prof[0] = (unsigned long long)(clock64() - t_begin); g_igemm_prof[1] = (unsigned long long)w_empty; }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
+    } else if (warp == 1 || (p.dual && warp == 11)) {
+        // ===================== MMA issuer (one thread per pipeline) =====================
         if (lane == 0) {
+            const int pipe = warp == 11 ? 1 : 0, npipes = p.dual ? 2 : 1;
+            uint64_t* const full_bar_p = full_bar + pipe * p.ring_stages;
+            uint64_t* const empty_bar_p = empty_bar + pipe * p.ring_stages;
+            const uint32_t ring = smem_u32(smem) + (uint32_t)(pipe * p.ring_stages * stage_bytes);
             int st = 0;
             uint32_t ph = 0;
-            int acc = 0;
+            int acc = pipe;            // dual: pipeline j owns accumulator j; single: the accumulators alternate
             uint32_t aph = 0;
-            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            const bool prof = (p.dbg & 16) && blockIdx.x == 0 && pipe == 0;
             long long w_tempty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += npipes * gridDim.x) {
                 long long t0 = prof ? clock64() : 0;
                 mbar_wait(&tempty_bar[acc], aph ^ 1);
                 if (prof) w_tempty += clock64() - t0;
@@ -334,10 +348,10 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
                 for (int ks = 0; ks < ksteps; ++ks) {
                     t0 = prof ? clock64() : 0;
-                    mbar_wait(&full_bar[st], ph);
+                    mbar_wait(&full_bar_p[st], ph);
                     if (prof) w_full += clock64() - t0;
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sa = ring + (uint32_t)(st * stage_bytes);
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
                     const uint64_t db = umma_desc_kmajor_sw128(sa + kABytes);
                     // merged split precision: k-steps alternate (per K-chunk run) between N = 2*BN and N = BN
@@ -350,18 +364,19 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         else
                             umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[st]);  // frees the smem stage when these MMAs retire
-                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                    umma_commit(&empty_bar_p[st]);  // frees the smem stage when these MMAs retire
+                    if (++st == p.ring_stages) { st = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; aph ^= 1; }
+                if (p.dual) aph ^= 1;
+                else if (++acc == 2) { acc = 0; aph ^= 1; }
             }
             if (prof) {
                 g_igemm_prof[2] = (unsigned long long)(clock64() - t_begin);
                 g_igemm_prof[3] = (unsigned long long)w_tempty; g_igemm_prof[4] = (unsigned long long)w_full;
             }
         }
-    } else if (p.epi_impl == 1) {
+    } else if (warp >= 2 && warp < 2 + kNumEpiWarps && p.epi_impl == 1) {
         // ===================== epilogue warps: transposed, coalesced =====================
         // TMEM gives each lane one accumulator ROW (pixel).  The raw accumulators of a 16/32-channel chunk
         // are dumped to a warp-private smem scratch and read back transposed, so that in the arithmetic and
@@ -586,7 +601,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             g_igemm_prof[o] = (unsigned long long)(clock64() - t_begin); g_igemm_prof[o + 1] = (unsigned long long)w_tfull;
             g_igemm_prof[o + 2] = (unsigned long long)busy; g_igemm_prof[o + 3] = (unsigned long long)ntile;
         }
-    } else {
+    } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
         // ===================== epilogue warps (row-per-lane reference implementation) =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;           // TMEM lane quarter this warp may access
@@ -862,7 +877,15 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         if (stages_cap > 0 && stages > stages_cap) stages = stages_cap;
         p.stages = stages;
         ring_bytes = (size_t)stages * stage_bytes;
+        // dual pipelines for thin N (one issuing thread cannot feed the tensor pipe below N = 256); MG_DUAL=0 disables
+        const int dual_env = getenv("MG_DUAL") ? atoi(getenv("MG_DUAL")) : 1;
+        const int sms = num_sms();
+        if (dual_env && p.acc_cols <= 128 && stages >= 4 && p.num_tiles >= 2 * (a->max_ctas > 0 && a->max_ctas < sms ? a->max_ctas : sms)) {
+            p.dual = 1;
+            p.ring_stages = stages / 2;
+        }
     }
+    if (!p.dual) p.ring_stages = p.stages;
     p.bar_off = (int)ring_bytes;
     p.epi_off = (int)ring_bytes + 512;
     p.idesc2 = a->a_fmt == 0 ? umma_idesc_tf32(128, BN) : umma_idesc_16(128, BN, a->a_fmt);

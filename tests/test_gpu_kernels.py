@@ -87,6 +87,39 @@ def test_igemm_16bit_operands(gen, N, h, Cin, Cout, k, s, p):
         assert rel_err(nchw(got), ref32) <= 6e-5, merge
 
 
+@pytest.mark.parametrize("fmt", ["tf32", "bf3"])
+def test_igemm_dual_pipelines(gen, fmt):
+    """Thin-N layers (accumulator <= 128 columns) with at least two tiles per CTA run two (TMA producer, MMA issuer) pairs on
+    alternate tiles / TMEM accumulators; max_ctas=3 forces that schedule at a small size (5 and 6 tiles per CTA, odd and
+    even), MG_DUAL=0 is the single-pipeline schedule of the same GEMM."""
+    ops = _ops()
+    N, h, Cin, Cout = 2, 32, 64, 64
+    x = torch.randn(N, Cin, h, h, generator=gen).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=gen) / 24).to(dev)
+    b = torch.randn(Cout, generator=gen).to(dev)
+    outs = {}
+    for dual in ("1", "0"):
+        os.environ["MG_DUAL"] = dual
+        try:
+            if fmt == "tf32":
+                xt, wt = tf32_trunc(x), tf32_trunc(w)
+                ref = F.conv2d(xt, wt, b, padding=1)
+                outs[dual] = ops.conv_igemm(nhwc(xt), ops.pack_weight(wt, None, round_tf32=True), Cout, 3, 3, 1, 1, bias=b, max_ctas=3)
+                tol = 2e-5
+            else:
+                xn = nhwc(x)
+                hi = xn.bfloat16()
+                lo = (xn - hi.float()).bfloat16()
+                ref = F.conv2d(x, w, b, padding=1)
+                outs[dual] = ops.conv_igemm(hi, ops.pack_weight16(w, None, ops.BF16, split=True), Cout, 3, 3, 1, 1, bias=b, a_fmt=ops.BF16,
+                                            x_lo=lo, max_ctas=3)
+                tol = 6e-5
+        finally:
+            os.environ.pop("MG_DUAL", None)
+        assert rel_err(nchw(outs[dual]), ref) <= tol, dual
+    assert torch.equal(outs["1"], outs["0"])   # same MMA order per output tile -> bit-identical
+
+
 def test_igemm_halo_mode_matches_classic(gen):
     """MG_HALO=1 (one input patch per K chunk, taps through shifted UMMA descriptors) is an alternative schedule of the
     same GEMM: results must agree with the classic per-tap loads to accumulation-order noise."""
