@@ -13,18 +13,22 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "mg_ptx.cuh"
 #include "mg_internal.h"
 
 namespace mg {
 
-constexpr int kWgThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+// warp 0: TMA producer, warp 1: MMA issuer 0, warps 2-5: epilogue, warp 6: MMA issuer 1 (filter taps are split between the
+// two issuers when KW >= 2: one thread cannot issue more than one small-N tcgen05.mma per ~100-120 cycles)
+constexpr int kWgThreads = 224;
 constexpr int kWgStagesMax = 6;
 
 struct WgradParams {
     int N, OH, OW, Cout, Cin, KH, KW, stride, pad;
     int TW, TH, TN, tiles_w, tiles_h, tiles_n, pix_tiles;
     int BN, m_tiles, n_tiles, splits, stages;
+    int issuers;               // 1 or 2 MMA-issuing threads (taps kw = j, j + issuers, ... belong to issuer j)
     int pix_tile, box_bytes;   // K (pixels) per pipeline stage: 32 or 64; bytes of one [pix_tile x 32 ch] box
     uint32_t idesc, tmem_cols;
     float* dw;  // [Cout][KH*KW*Cin]
@@ -73,8 +77,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmDY);
         tma_prefetch_desc(&tmX);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(done_bar, 1);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.issuers); }
+        mbar_init(done_bar, p.issuers);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
@@ -104,15 +108,16 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp == 1 || warp == 6) {
+        const int issuer = warp == 6 ? 1 : 0;
+        if (lane == 0 && issuer < p.issuers) {
             int st = 0; uint32_t ph = 0;
             uint32_t first = 1;
             for (int t = t_begin; t < t_end; ++t) {
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-                for (int kw = 0; kw < p.KW; ++kw)
+                for (int kw = issuer; kw < p.KW; kw += p.issuers)
                     for (int k = 0; k < p.pix_tile / 8; ++k) {
                         const uint64_t da = umma_desc_mnmajor_sw128(sa + k * 1024, kBoxBytes);
                         const uint64_t db = umma_desc_mnmajor_sw128(sa + a_bytes + kw * b1_bytes + k * 1024, kBoxBytes);
@@ -124,7 +129,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             }
             umma_commit(done_bar);
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;  // output channel within the M tile
         const int co = mt * 128 + row;
@@ -188,6 +193,8 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
     p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.m_tiles = (Cout + 127) / 128;
     p.n_tiles = Cin / BN;
+    static const int dual_env = getenv("MG_WGRAD_DUAL") ? atoi(getenv("MG_WGRAD_DUAL")) : 1;
+    p.issuers = (KW >= 2 && dual_env) ? 2 : 1;
     const int units = KH * p.m_tiles * p.n_tiles;
     int splits = (2 * num_sms() + units - 1) / units;
     if (splits > p.pix_tiles) splits = p.pix_tiles;
