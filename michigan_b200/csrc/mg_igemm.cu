@@ -878,9 +878,11 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         p.stages = stages;
         ring_bytes = (size_t)stages * stage_bytes;
         // dual pipelines for thin N (one issuing thread cannot feed the tensor pipe below N = 256); MG_DUAL=0 disables
+        // MG_DUAL=2 (experiment) also splits N = 256 layers, whose ring is then only 2 + 2 stages deep
         const int dual_env = getenv("MG_DUAL") ? atoi(getenv("MG_DUAL")) : 1;
         const int sms = num_sms();
-        if (dual_env && p.acc_cols <= 128 && stages >= 4 && p.num_tiles >= 2 * (a->max_ctas > 0 && a->max_ctas < sms ? a->max_ctas : sms)) {
+        const int dual_cols = dual_env >= 2 ? 256 : 128;
+        if (dual_env && p.acc_cols <= dual_cols && stages >= 4 && p.num_tiles >= 2 * (a->max_ctas > 0 && a->max_ctas < sms ? a->max_ctas : sms)) {
             p.dual = 1;
             p.ring_stages = stages / 2;
         }
