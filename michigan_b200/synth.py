@@ -48,6 +48,10 @@ def fill_state_dict(sd, seed=0, power_iters=30):
         if key.endswith("weight_u"):
             base = key[: -len("weight_u")]
             w = sd[base + "weight_orig"].detach().double().cpu()
+            # torch's spectral_norm flattens around dim 0, or dim 1 for ConvTranspose (InpaintGenerator's decoder,
+            # generator.py:539-545): recognisable by the length of the stored u
+            if sd[key].numel() != w.shape[0] and w.dim() > 1 and sd[key].numel() == w.shape[1]:
+                w = w.transpose(0, 1)
             mat = w.reshape(w.shape[0], -1)
             u = torch.from_numpy(_rs(seed, key).standard_normal(mat.shape[0]))
             u = u / u.norm()

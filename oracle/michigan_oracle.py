@@ -421,3 +421,76 @@ def compute_discriminator_loss(sdG, sdD, opt, data, **kw):
 def trainer_loss(losses):
     """Pix2PixTrainer: sum(losses.values()).mean() (pix2pix_trainer.py:42,66)."""
     return sum(losses.values()).mean()
+
+
+# ----------------------------------------------------------------------------------------------- orientation inpainting
+# SURVEY.md §8 row a16 ("next"): InpaintGenerator (generator.py:450-575) + Pix2PixModel.inpainting_orient
+# (pix2pix_model.py:407-429).  The network is frozen and always runs in eval mode (pix2pix_model.py:196-198).
+def spectral_weight_eval(sd, prefix, dim=0):
+    """Eval-mode spectral norm: W_orig / (u^T W_mat v) with the stored u, v and no power iteration
+    (torch/nn/utils/spectral_norm.py `compute_weight(do_power_iteration=False)`); `dim` = 1 for ConvTranspose2d."""
+    w = sd[prefix + ".weight_orig"]
+    u = sd[prefix + ".weight_u"]
+    v = sd[prefix + ".weight_v"]
+    mat = w if dim == 0 else w.transpose(0, dim)
+    mat = mat.reshape(mat.shape[0], -1)
+    sigma = torch.dot(u, torch.mv(mat, v))
+    return w / sigma
+
+
+def _in(x):
+    return F.instance_norm(x, eps=1e-5)   # nn.InstanceNorm2d(dim): affine=False, no running stats
+
+
+def inpaint_resnet_block(x, sd, prefix):
+    """ResnetBlock (generator.py:450-465): x + IN(conv3x3(reflpad1(ReLU(IN(conv3x3 dil2(reflpad2(x)))))))."""
+    h = F.conv2d(F.pad(x, (2, 2, 2, 2), mode="reflect"), spectral_weight_eval(sd, prefix + ".conv_block.1"),
+                 sd[prefix + ".conv_block.1.bias"], dilation=2)
+    h = F.relu(_in(h))
+    h = F.conv2d(F.pad(h, (1, 1, 1, 1), mode="reflect"), spectral_weight_eval(sd, prefix + ".conv_block.5"),
+                 sd[prefix + ".conv_block.5.bias"])
+    return x + _in(h)
+
+
+def inpaint_self_attention(x, sd, prefix):
+    """SelfAttention (generator.py:468-487): softmax(q^T k) over keys, value projected back, concatenated to x."""
+    n, c, a, b = x.shape
+    q = F.conv2d(x, sd[prefix + ".query_conv.weight"], sd[prefix + ".query_conv.bias"]).view(n, -1, a * b).permute(0, 2, 1)
+    k = F.conv2d(x, sd[prefix + ".key_conv.weight"], sd[prefix + ".key_conv.bias"]).view(n, -1, a * b)
+    attn = torch.softmax(torch.bmm(q, k), dim=-1)
+    v = F.conv2d(x, sd[prefix + ".value_conv.weight"], sd[prefix + ".value_conv.bias"]).view(n, -1, a * b)
+    out = torch.bmm(v, attn.permute(0, 2, 1)).view(n, c, a, b)
+    return torch.cat([x, out], dim=1)
+
+
+def inpaint_generator(x, sd, blocks=12):
+    """InpaintGenerator.forward, skips=False (generator.py:490-575): [N,4,H,W] -> [N,3,H,W] in [0,1]."""
+    h = F.conv2d(F.pad(x, (3, 3, 3, 3), mode="reflect"), spectral_weight_eval(sd, "encoder.1"), sd["encoder.1.bias"])
+    h = lrelu(_in(h))
+    h = lrelu(_in(F.conv2d(h, spectral_weight_eval(sd, "encoder.4"), sd["encoder.4.bias"], stride=2, padding=1)))
+    h = lrelu(_in(F.conv2d(h, spectral_weight_eval(sd, "encoder.7"), sd["encoder.7.bias"], stride=2, padding=1)))
+    for i in range(blocks):
+        h = inpaint_resnet_block(h, sd, "middle.%d" % i)
+    h = inpaint_self_attention(h, sd, "middle.%d" % blocks)
+    h = F.conv_transpose2d(h, spectral_weight_eval(sd, "decoder.0", dim=1), sd["decoder.0.bias"], stride=2, padding=1)
+    h = F.relu(_in(h))
+    h = F.conv_transpose2d(h, spectral_weight_eval(sd, "decoder.3", dim=1), sd["decoder.3.bias"], stride=2, padding=1)
+    h = F.relu(_in(h))
+    h = F.conv2d(F.pad(h, (3, 3, 3, 3), mode="reflect"), sd["decoder.7.weight"], sd["decoder.7.bias"])
+    return (torch.tanh(h) + 1) / 2
+
+
+def inpainting_orient(sd_ig, crop_size, hole, orient_rgb, noise, mask):
+    """Pix2PixModel.inpainting_orient (pix2pix_model.py:407-429): fill the hole of the orientation RGB map with the
+    frozen inpainting net (run at 256x256, nearest resize both ways) and convert it to the 2-channel orientation
+    (cos 2theta, sin 2theta swapped into the generator's order) masked by the hair mask.  Returns (output, orient)."""
+    inp = torch.cat([orient_rgb * (1 - hole) + noise * hole, hole], dim=1)
+    if crop_size != 256:
+        inp = F.interpolate(inp, size=(256, 256), mode="nearest")
+    out = inpaint_generator(inp, sd_ig)
+    if crop_size != 256:
+        out = F.interpolate(out, size=(crop_size, crop_size), mode="nearest")
+    out = out * hole + orient_rgb * (1 - hole)
+    o2 = (out[:, :-1] - 0.5) * 2
+    orient = torch.stack([o2[:, 1], o2[:, 0]], dim=1) * mask
+    return out, orient
