@@ -9,10 +9,11 @@ from .architecture import SPADEResnetBlock
 from .encoder import ImageEncoder3, BackgroundEncode2, PartialConv2d, ConvBlock
 from .generator import SPADEBGenerator
 from .discriminator import MultiscaleDiscriminator, NLayerDiscriminator
+from .inpaint import InpaintGenerator
 from . import sync_batchnorm
 from .sync_batchnorm import SynchronizedBatchNorm2d, DataParallelWithCallback
 
-_GENERATORS = {"spadeb": SPADEBGenerator}
+_GENERATORS = {"spadeb": SPADEBGenerator, "inpaint": InpaintGenerator}
 _DISCRIMINATORS = {"multiscale": MultiscaleDiscriminator, "nlayer": NLayerDiscriminator, "n_layer": NLayerDiscriminator}
 
 
@@ -46,6 +47,11 @@ def create_network(cls, opt):
 
 def define_G(opt):
     return create_network(find_network_using_name(opt.netG, "generator"), opt)
+
+
+def define_IG(opt):
+    """networks/__init__.py:70-72 (`--netIG inpaint`): the frozen orientation-inpainting net of --use_ig."""
+    return create_network(find_network_using_name(getattr(opt, "netIG", "inpaint"), "generator"), opt)
 
 
 def define_D(opt):

@@ -29,8 +29,14 @@ class Pix2PixModel(torch.nn.Module):
         for flag in ("use_vae", "use_blender", "use_instance_feat", "unpairTrain"):
             if getattr(opt, flag, False):
                 raise NotImplementedError("michigan_b200: --%s is outside the hot path (SURVEY.md §8)" % flag)
+        self.netIG = None
         if getattr(opt, "use_ig", False):
-            raise NotImplementedError("michigan_b200: --use_ig (orientation inpainting net) is a 'next' row (SURVEY.md §8f)")
+            from .networks import inpaint
+            if not inpaint.experimental_enabled():
+                raise NotImplementedError("michigan_b200: --use_ig (orientation inpainting net) is a 'next' row (SURVEY.md §8f); its "
+                                          "CUDA composition exists but is not GPU-validated yet - set MICHIGAN_B200_EXPERIMENTAL_IG=1 to try it")
+            self.netIG = networks.define_IG(opt)
+            self._load_inpainting_network(opt)
         self.netG = networks.define_G(opt)
         self.netD = networks.define_D(opt) if opt.isTrain else None
         if opt.isTrain:
@@ -60,9 +66,35 @@ class Pix2PixModel(torch.nn.Module):
         if self.netD is not None:
             torch.save({k: v.cpu() for k, v in self.netD.state_dict().items()}, self._ckpt_path("D", epoch))
 
+    def _load_inpainting_network(self, opt):
+        """util.load_inpainting_network (util.py:245-257): <checkpoints_dir>/<name>/<ig_model_name> = {'generator': state_dict}."""
+        path = os.path.join(getattr(opt, "checkpoints_dir", "."), getattr(opt, "name", ""), getattr(opt, "ig_model_name", "InpaintingModel_gen.pth"))
+        data = torch.load(path, map_location="cpu")
+        self.netIG.load_state_dict(data["generator"])
+        self.netIG.eval()
+
+    def inpainting_orient(self, hole, orient_rgb, noise, mask):
+        """pix2pix_model.py:407-429: fill the hole of the orientation RGB map with the frozen net (run at 256x256, nearest
+        resize both ways) and derive the generator's 2-channel orientation input, masked by the hair mask."""
+        inp = torch.cat([orient_rgb * (1 - hole) + noise * hole, hole], dim=1)
+        if self.opt.crop_size != 256:
+            inp = F.interpolate(inp, size=(256, 256), mode="nearest")
+        out = self.netIG(inp)
+        if self.opt.crop_size != 256:
+            out = F.interpolate(out, size=(self.opt.crop_size, self.opt.crop_size), mode="nearest")
+        out = out * hole + orient_rgb * (1 - hole)
+        o2 = (out[:, :-1] - 0.5) * 2
+        return out, (torch.stack([o2[:, 1], o2[:, 0]], dim=1) * mask).contiguous()
+
     # ------------------------------------------------------------------ entry point
     def forward(self, data, mode):
         input_ref, input_tag, image_ref, image_tag, orient_mask, noise = self.preprocess_input(data)
+        if self.netIG is not None:
+            # pix2pix_model.py:260-263 / 370-372: the 2-channel inpainted orientation replaces the 1-channel angle map
+            dev = input_tag.device
+            with torch.no_grad():
+                _, orient_mask = self.inpainting_orient(data["hole"].to(dev).float(), data["orient_rgb"].to(dev).float(), noise,
+                                                        input_tag[:, 1:2])
         if mode == "generator":
             return self.compute_generator_loss(input_ref, input_tag, image_ref, image_tag, orient_mask, noise)
         if mode == "discriminator":

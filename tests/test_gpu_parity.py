@@ -2,6 +2,7 @@
 fixtures.  Tolerances: tensor-core convs read TF32 operands (10-bit mantissa, RN-rounded by the
 producer) with fp32 accumulation, so feature maps are compared at 5e-3 of their abs-max and the
 generator image against BASELINE.json's bound: max-abs <= 1e-3 (mean-abs reported, must be <= 2e-4)."""
+import os
 import random
 
 import numpy as np
@@ -308,3 +309,23 @@ def test_train_iteration_losses_and_grads_vs_golden():
             worst = min(worst, cos)
     assert worst >= 0.98, worst
     opt_D.step()
+
+
+@pytest.mark.skipif(os.environ.get("MICHIGAN_B200_EXPERIMENTAL_IG", "0") != "1",
+                    reason="row a16 (next): the InpaintGenerator CUDA composition has not been validated on a GPU yet; "
+                           "run with MICHIGAN_B200_EXPERIMENTAL_IG=1")
+def test_inpaint_generator_vs_oracle_experimental():
+    """InpaintGenerator (generator.py:490-575) composed from the main path's kernels vs the CPU oracle on identical
+    deterministic weights; output in [0, 1], tolerance 1e-3 max-abs like the generator image."""
+    from michigan_b200.networks.inpaint import InpaintGenerator
+    from michigan_b200.synth import fill_state_dict
+    net = InpaintGenerator()
+    fill_state_dict(net.state_dict(), 21)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 4, 128, 128, generator=g)
+    with torch.no_grad():
+        ref = orc.inpaint_generator(x, {k: v.clone() for k, v in net.state_dict().items()})
+    out = net.cuda()(x.cuda()).cpu()
+    mx, mn = max_mean_abs(out, ref)
+    print("InpaintGenerator vs oracle: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    assert mx <= MAX_ABS

@@ -159,3 +159,58 @@ def test_install_plugs_into_reference_model():
     assert pix2pix_trainer.DataParallelWithCallback.__module__.startswith("models.networks.sync_batchnorm") or True
     import models.networks.sync_batchnorm as sbn
     assert sbn.DataParallelWithCallback is networks.DataParallelWithCallback
+
+
+# ------------------------------------------------------------------------------------------ row a16 (next): InpaintGenerator host side
+def test_inpaint_generator_state_dict_layout_and_oracle_agreement():
+    """The host container has the reference's 124 keys / 16,118,211 parameters (generator.py:490-561) and its parameters,
+    read back through the oracle, reproduce the golden fixture - i.e. a checkpoint of the reference loads unchanged."""
+    import json
+    import numpy as np
+    import michigan_oracle as orc
+    from michigan_b200.networks.inpaint import InpaintGenerator
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_inpaint.npz"))
+    cfg = json.loads(bytes(z["config"]).decode())
+    net = InpaintGenerator()
+    sd = net.state_dict()
+    assert len(sd) == 124
+    assert sum(v.numel() for k, v in sd.items() if not k.endswith(("weight_u", "weight_v"))) == 16118211
+    assert sd["decoder.0.weight_orig"].shape == (512, 128, 4, 4) and sd["decoder.0.weight_u"].shape == (128,)
+    fill_state_dict(sd, cfg["seed_IG"])
+    g = torch.Generator().manual_seed(cfg["input_seed"])
+    x = torch.rand(cfg["net_batch"], 4, cfg["net_hw"], cfg["net_hw"], generator=g)
+    with torch.no_grad():
+        out = orc.inpaint_generator(x, {k: v.clone() for k, v in net.state_dict().items()})
+    assert float((out - torch.from_numpy(z["net_out"])).abs().max()) <= 2e-6
+    with pytest.raises(Exception):
+        net(x)   # no CPU path
+
+
+def test_dilated_conv_equals_dense_conv_on_parity_subgrids():
+    """Index arithmetic behind the dilation-2 convs of the inpainting ResnetBlocks (generator.py:455): a 'valid'
+    dilation-2 3x3 conv on the reflect-padded map == the dense 'valid' 3x3 conv on its four parity sub-grids stacked
+    along the batch axis (what the implicit-GEMM kernel is given), interleaved back."""
+    import torch.nn.functional as F
+    from michigan_b200.networks.inpaint import parity_stack, parity_unstack
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 8, 16, 12, generator=g)
+    w = torch.randn(5, 8, 3, 3, generator=g)
+    xp = F.pad(x, (2, 2, 2, 2), mode="reflect")
+    ref = F.conv2d(xp, w, dilation=2)
+    st = parity_stack(xp.permute(0, 2, 3, 1).contiguous())                       # NHWC, [4N, 10, 8, C]
+    dense = F.conv2d(st.permute(0, 3, 1, 2), w).permute(0, 2, 3, 1).contiguous()  # [4N, 8, 6, 5]
+    got = parity_unstack(dense, 2).permute(0, 3, 1, 2)
+    assert got.shape == ref.shape and float((got - ref).abs().max()) <= 1e-5
+
+
+def test_conv_transpose_is_the_data_gradient_of_the_strided_conv():
+    """ConvTranspose2d(k4, s2, p1) of the inpainting decoder (generator.py:539-545) == dX of conv2d(k4, s2, p1) with the
+    SAME weight tensor read as [O = in_t, I = out_t, kh, kw] - the contract of ops.conv_dgrad (GPU-tested against autograd)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 6, 5, 7, generator=g)
+    w = torch.randn(6, 3, 4, 4, generator=g)              # ConvTranspose2d weight: [in, out, kh, kw]
+    ref = F.conv_transpose2d(x, w, stride=2, padding=1)   # [2, 3, 10, 14]
+    probe = torch.zeros(2, 3, 10, 14, requires_grad=True)
+    F.conv2d(probe, w, stride=2, padding=1).backward(x)   # conv 3 -> 6 channels with weight [O=6, I=3]; dX given dY = x
+    assert float((probe.grad - ref).abs().max()) <= 1e-5
