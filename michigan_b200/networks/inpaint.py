@@ -139,6 +139,9 @@ class InpaintGenerator(BaseNetwork):
             raise RuntimeError("InpaintGenerator is a frozen network: call .eval() (pix2pix_model.py:196-198)")
         if not x.is_cuda:
             raise ops._lib.MichiganNativeError("InpaintGenerator has no CPU path")
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x):
         enc, mid, dec = self.encoder, self.middle, self.decoder
         n = x.shape[0]
         with torch.no_grad():

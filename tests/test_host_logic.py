@@ -214,3 +214,92 @@ def test_conv_transpose_is_the_data_gradient_of_the_strided_conv():
     probe = torch.zeros(2, 3, 10, 14, requires_grad=True)
     F.conv2d(probe, w, stride=2, padding=1).backward(x)   # conv 3 -> 6 channels with weight [O=6, I=3]; dX given dY = x
     assert float((probe.grad - ref).abs().max()) <= 1e-5
+
+
+def test_inpaint_forward_glue_with_torch_standins(monkeypatch):
+    """The Python glue of InpaintGenerator's CUDA composition (operand plumbing, parity stacking of the dilated convs,
+    residuals, attention layout, transposed convs through the dgrad entry point, 3-of-32-channel head) checked on the CPU:
+    the C-ABI wrappers it calls are replaced by torch stand-ins WITH THE SAME SIGNATURES (test-only; the product has no
+    CPU path), and the result must match the oracle.  What this cannot cover - the kernels themselves - is covered for
+    each entry point by the GPU parity tests of the main path."""
+    import numpy as np
+    import torch.nn.functional as F
+    from types import SimpleNamespace
+    import michigan_oracle as orc
+    from michigan_b200.networks import inpaint
+
+    TF32, F16, BF16 = 0, 1, 2
+    ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+    def act_fn(y, act):
+        return F.relu(y) if act == ACT_RELU else (F.leaky_relu(y, 0.2) if act == ACT_LRELU else y)
+
+    def split16(y, out16):
+        fmt, want_lo = out16
+        hi = y.to(torch.bfloat16 if fmt == BF16 else torch.float16)
+        return hi, ((y - hi.float()).to(hi.dtype) if want_lo else None)
+
+    def nchw(t):
+        return t.permute(0, 3, 1, 2)
+
+    def nhwc(t):
+        return t.permute(0, 2, 3, 1).contiguous()
+
+    def nchw_to_nhwc(x, cpad=None):
+        y = nhwc(x)
+        if cpad and cpad > y.shape[-1]:
+            y = F.pad(y, (0, cpad - y.shape[-1]))
+        return y
+
+    def conv_thin(x, wt, bias, cout, kh, kw, stride=1, pad=0, *, pad_mode=0, **kw_):
+        assert pad_mode == 1 and wt.shape[0] == cout
+        xp = F.pad(nchw(x)[:, :wt.shape[1]], (pad, pad, pad, pad), mode="reflect")
+        return nhwc(F.conv2d(xp, wt, bias, stride=stride))
+
+    def instance_norm_act(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None, out16=None, want_f32=True):
+        y = nhwc(act_fn(F.instance_norm(nchw(x), eps=eps), act))
+        if out16 is not None:
+            hi, lo = split16(y, out16)
+            return (y if want_f32 else None), hi, lo
+        return y
+
+    def reflect_pad(x, pad, round_tf32=False, out16=None, want_f32=True):
+        y = nhwc(F.pad(nchw(x), (pad, pad, pad, pad), mode="reflect")) if pad else x
+        if out16 is not None:
+            hi, lo = split16(y, out16)
+            return (y if want_f32 else None), hi, lo
+        return y
+
+    def conv_dgrad(dy, w_oihw, in_hw, stride=1, pad=0, inv_sigma=None, out=None, accumulate=False):
+        w = w_oihw * (inv_sigma if inv_sigma is not None else 1.0)
+        y = F.conv_transpose2d(nchw(dy), w, stride=stride, padding=pad)
+        assert tuple(y.shape[2:]) == tuple(in_hw)
+        return nhwc(y)
+
+    fake_ops = SimpleNamespace(TF32=TF32, F16=F16, BF16=BF16, ACT_NONE=ACT_NONE, ACT_RELU=ACT_RELU, ACT_LRELU=ACT_LRELU,
+                               nchw_to_nhwc=nchw_to_nhwc, pack_weight_thin=lambda w, cinp: w, conv_thin=conv_thin,
+                               instance_norm_act=instance_norm_act, reflect_pad=reflect_pad, conv_dgrad=conv_dgrad)
+
+    def pack_conv(w, inv_sigma, fmt):
+        return w * (inv_sigma if inv_sigma is not None else 1.0)
+
+    def conv(operand, wpack, cout, kh, kw, stride, pad, bias=None, **kw_):
+        fmt, hi, lo = operand
+        x = hi.float() + (lo.float() if lo is not None else 0.0)
+        assert wpack.shape[0] == cout and wpack.shape[2] == kh
+        return nhwc(F.conv2d(nchw(x), wpack, bias, stride=stride, padding=pad))
+
+    for fmt_mode in (BF16, TF32):
+        fake_prec = SimpleNamespace(conv_fmt=lambda c, m=fmt_mode: m, pack_conv=pack_conv, conv=conv)
+        monkeypatch.setattr(inpaint, "ops", fake_ops)
+        monkeypatch.setattr(inpaint, "precision", fake_prec)
+        net = inpaint.InpaintGenerator()
+        fill_state_dict(net.state_dict(), 21)
+        g = torch.Generator().manual_seed(5)
+        x = torch.rand(2, 4, 32, 32, generator=g)
+        with torch.no_grad():
+            got = net._forward_impl(x)
+            ref = orc.inpaint_generator(x, {k: v.clone() for k, v in net.state_dict().items()})
+        assert got.shape == ref.shape
+        err = float((got - ref).abs().max())
+        assert err <= (2e-4 if fmt_mode == BF16 else 1e-4), (fmt_mode, err)   # bf16 hi+lo operands / fp32 reassociation
