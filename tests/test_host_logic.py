@@ -303,3 +303,31 @@ def test_inpaint_forward_glue_with_torch_standins(monkeypatch):
         assert got.shape == ref.shape
         err = float((got - ref).abs().max())
         assert err <= (2e-4 if fmt_mode == BF16 else 1e-4), (fmt_mode, err)   # bf16 hi+lo operands / fp32 reassociation
+
+
+def test_bench_reference_arm_json_contract(monkeypatch, capsys):
+    """`bench.py --impl reference` prints ONE JSON line with the contract's keys (the CPU work itself is stubbed here:
+    it is timed for real on the GPU box's host cores)."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"])
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "cpu_generator_forward_ips", lambda steps, warm, n: (0.25, 4000.0, 16))
+    monkeypatch.delenv("RANK", raising=False)
+    bench.run_reference_arm(bench.parse())
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 16 and "workload" in d["config"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 print nothing
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference_arm(bench.parse())
+    assert capsys.readouterr().out.strip() == ""
