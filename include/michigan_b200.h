@@ -11,8 +11,11 @@
  *     allocates device memory; work is enqueued on `stream`;
  *   - return 0 on success, <0 for a rejected argument, >0 = cudaError_t; mg_last_error() gives the
  *     message of the calling thread's last failure;
- *   - re-entrant across host threads and devices (no global mutable state besides a per-thread
- *     error string and a one-time driver entry-point lookup).
+ *   - re-entrant across host threads and devices.  Global state: a per-thread error string, a
+ *     per-thread cache of TMA descriptors, a one-time driver entry-point lookup and the schedule
+ *     knobs of mg_set_tuning (read once from the environment; every setting gives the same results).
+ *     The what-if probes that skip work (env MG_DBG) exist only in the -DMG_PROBES build used by
+ *     tools/; the product library has no switch that changes results.
  */
 #ifndef MICHIGAN_B200_H
 #define MICHIGAN_B200_H
@@ -27,7 +30,12 @@ int mg_version(void);
 const char* mg_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 long long mg_launch_count(void);
-/* debugging aid: 16 clock64() totals CTA 0 of mg_conv_igemm recorded under env MG_DBG=16 (producer / MMA / epilogue waits) */
+/* Schedule knobs ("MG_DUAL", "MG_MERGE", "MG_HALO", "MG_HALO_PW", "MG_EPI_IMPL", "MG_EPI_IMPL_SPADE", "MG_EPI_CW16",
+ * "MG_EPI_CW_SPADE", "MG_STAGES", "MG_WGRAD_DUAL", "MG_THIN_GEMM", "MG_THIN_WGRAD_LEGACY"): initialised once from the
+ * environment variable of the same name, changed here by tests and A/B tools.  Unknown name: -2 / -1. */
+int mg_set_tuning(const char* name, int value);
+int mg_get_tuning(const char* name);
+/* debugging aid (probe build only, zeros otherwise): 16 clock64() totals CTA 0 of mg_conv_igemm recorded under env MG_DBG=16 */
 int mg_debug_igemm_prof(unsigned long long* host16);
 
 /* activation codes */

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmichigan_sm100.so")
+# MICHIGAN_B200_LIB: tools/ select the -DMG_PROBES build (timing experiments); the product always loads the in-tree release library
+LIB_PATH = os.environ.get("MICHIGAN_B200_LIB") or os.path.join(_HERE, "lib", "libmichigan_sm100.so")
 
 c_f32p = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
 
@@ -56,6 +57,8 @@ SIGNATURES = {
     "mg_version": [],
     "mg_last_error": [],
     "mg_launch_count": [],
+    "mg_set_tuning": [C.c_char_p, _i],
+    "mg_get_tuning": [C.c_char_p],
     "mg_debug_igemm_prof": [C.c_void_p],
     "mg_conv_igemm": [C.POINTER(IgemmArgs), _p],
     "mg_pack_weight": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
@@ -139,6 +142,14 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().mg_last_error().decode("utf-8", "replace")
         raise MichiganNativeError("%s failed (status %d): %s" % (what or "libmichigan_sm100 call", rc, msg))
+
+
+def set_tuning(name, value):
+    """Schedule knob of the library (see mg_set_tuning in the header); returns the previous value."""
+    lib = load()
+    prev = lib.mg_get_tuning(name.encode())
+    check(lib.mg_set_tuning(name.encode(), int(value)), "mg_set_tuning")
+    return prev
 
 
 def launch_count():

@@ -37,9 +37,12 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
-    if not force and not _stale():
+def build(force=False, verbose=False, probes=False):
+    """Compile every CUDA source for sm_100a and link the shared library. Returns its path.
+    probes=True builds the tools-only variant libmichigan_sm100_probes.so (-DMG_PROBES: what-if switches that skip work
+    and the clock64() role profiles; never loaded by the product, select it with MICHIGAN_B200_LIB=<path>)."""
+    lib_path = LIB_PATH.replace(".so", "_probes.so") if probes else LIB_PATH
+    if not force and not probes and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
@@ -49,8 +52,8 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, s)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(LIB_DIR, s.replace(".cu", ".o"))
-        cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")], "-c", src, "-o", obj]
+        obj = os.path.join(LIB_DIR, s.replace(".cu", "_probes.o" if probes else ".o"))
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")], *(["-DMG_PROBES"] if probes else []), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -61,12 +64,12 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-cudart", "static"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv))

@@ -931,7 +931,7 @@ extern "C" int mg_conv_thin(const mg_thin_args* a, void* stream) {
         if (e != cudaSuccess) return set_error((int)e, "thin attr: %s", cudaGetErrorString(e));              \
         thin_conv_kernel<CI, CP><<<grid, 256, smem, ST(stream)>>>(*a, tiles_w, tiles_h, num_tiles);          \
     } while (0)
-    static const int use_gemm = getenv("MG_THIN_GEMM") ? atoi(getenv("MG_THIN_GEMM")) : 1;
+    const int use_gemm = tune(TK_THIN_GEMM);
     // measured on B200: the register-tiled variant wins for Cout = 64 (k7 / k4 layers), the lane-per-channel one for Cout = 128
     if ((use_gemm == 2 && a->Cout == 128) || (use_gemm >= 1 && a->Cout == 64)) {
 #define LAUNCH_TG(CI, CT)                                                                                     \

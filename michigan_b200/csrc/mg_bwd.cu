@@ -930,7 +930,7 @@ extern "C" int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N,
     // register-tiled kernel: Cout 64/128, columns per thread = ceil(K / (256 / (Cout/4)))
     const int CG = Cout == 64 || Cout == 128 ? 256 / (Cout / 4) : 0;
     const int kpt = CG ? (K + CG - 1) / CG : 0;
-    static const bool legacy = getenv("MG_THIN_WGRAD_LEGACY") && atoi(getenv("MG_THIN_WGRAD_LEGACY")) != 0;
+    const bool legacy = tune(TK_THIN_WGRAD_LEGACY) != 0;
     if (CG && kpt <= 13 && CinP % 4 == 0 && !legacy) {
         const size_t smem = ((((size_t)PH * PW * CinP + 3) & ~(size_t)3) + 128 * (size_t)Cout) * 4;
         // load -> sync -> compute per tile: co-resident CTAs overlap one's loads with another's FMAs

@@ -69,7 +69,7 @@ struct IgemmParams {
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
     int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default); scratch offset in smem
     // halo mode (3x3, stride 1, pad 1): one [PW x (TH+2)] input patch per K chunk serves all 9 taps
-    int halo, PW, patch_bytes, patch_tx, a_slots, b_slots, b_slot_bytes, acc_cols, merged, n_items, bo_mode, bar_off;
+    int halo, PW, patch_bytes, patch_tx, a_slots, b_slots, b_slot_bytes, acc_cols, merged, n_items, bar_off;
     uint32_t idesc2;
     // dual mode: a single thread issues at most one tcgen05.mma per ~100-120 cycles whatever its N (microbenchmark
     // profiles/r01_mma_rate_two_issuers.log: N=64 120 -> 62 cycles/MMA with two issuers, N=128 120 -> 85), so thin-N layers
@@ -181,7 +181,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t bph = 0, aphs = 0;
             long long a_issued = 0, b_item = 0;
             int tileA = blockIdx.x, itA = 0;
-            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            const bool prof = (MG_DBGV(p) & 16) && blockIdx.x == 0;
             long long w_empty = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
@@ -230,7 +230,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t b_ring = a_ring + (uint32_t)(p.a_slots * p.patch_bytes);
             int bs = 0, as_ = 0, acc = 0;
             uint32_t bph = 0, aphs = 0, aph = 0;
-            const bool prof = (p.dbg & 16) && blockIdx.x == 0;
+            const bool prof = (MG_DBGV(p) & 16) && blockIdx.x == 0;
             long long w_tempty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 long long t0 = prof ? clock64() : 0;
@@ -257,7 +257,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t a_addr = a_tap + (uint32_t)(k * 32);
-                            const uint64_t da = umma_desc_sw128_general(a_addr, (uint32_t)(p.PW * 128), p.bo_mode ? (a_addr >> 7) & 7u : 0u);
+                            const uint64_t da = umma_desc_sw128_general(a_addr, (uint32_t)(p.PW * 128), 0u);
                             const uint32_t accum = (it | tap | k) != 0 ? 1u : 0u;
                             if (p.a_fmt == 0) umma_tf32(d_tmem, da, db + (uint64_t)(2 * k), idesc, accum);
                             else umma_f16(d_tmem, da, db + (uint64_t)(2 * k), idesc, accum);
@@ -285,10 +285,10 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* const ring = smem + (size_t)pipe * p.ring_stages * stage_bytes;
             int st = 0;
             uint32_t ph = 0;
-            const bool prof = (p.dbg & 16) && blockIdx.x == 0 && pipe == 0;
+            const bool prof = (MG_DBGV(p) & 16) && blockIdx.x == 0 && pipe == 0;
             long long w_empty = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += npipes * gridDim.x) {
-                const bool ldA = !(p.dbg & 2) || tile == (int)blockIdx.x, ldB = !(p.dbg & 1) || tile == (int)blockIdx.x;
+                const bool ldA = !(MG_DBGV(p) & 2) || tile == (int)blockIdx.x, ldB = !(MG_DBGV(p) & 1) || tile == (int)blockIdx.x;
                 const int nt = tile % p.n_tiles;
                 const int m = tile / p.n_tiles;
                 const int tw = m % p.tiles_w;
@@ -338,7 +338,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t ph = 0;
             int acc = pipe;            // dual: pipeline j owns accumulator j; single: the accumulators alternate
             uint32_t aph = 0;
-            const bool prof = (p.dbg & 16) && blockIdx.x == 0 && pipe == 0;
+            const bool prof = (MG_DBGV(p) & 16) && blockIdx.x == 0 && pipe == 0;
             long long w_tempty = 0, w_full = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += npipes * gridDim.x) {
                 long long t0 = prof ? clock64() : 0;
@@ -404,7 +404,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ch_tile = p.BN >> 1;
         int acc = 0;
         uint32_t aph = 0;
-        const bool prof = (p.dbg & 16) && blockIdx.x == 0 && (ew == 0 || ew == 7) && lane == 0;
+        const bool prof = (MG_DBGV(p) & 16) && blockIdx.x == 0 && (ew == 0 || ew == 7) && lane == 0;
         long long w_tfull = 0, busy = 0, t_begin = prof ? clock64() : 0;
         int ntile = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -435,7 +435,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
             for (int cb = 0; cb < span; cb += cw) {
-                if (p.dbg & 4) break;
+                if (MG_DBGV(p) & 4) break;
                 const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
                 float4 av[passes], bv[passes], pre[passes];
                 const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
@@ -484,7 +484,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // Per-pixel side loads (SPADE: the tensor being normalised; else the residual): issued as soon as the first
                 // transposition has freed its registers, so their L2 latency overlaps the second one.
                 const float* side = spade ? p.x : p.res;
-                if (side != nullptr && ch_ok && !(p.dbg & (8 | 64))) {
+                if (side != nullptr && ch_ok && !(MG_DBGV(p) & (8 | 64))) {
 #pragma unroll
                     for (int j = 0; j < passes; ++j)
                         if ((vmask >> j) & 1u) pre[j] = __ldg(reinterpret_cast<const float4*>(side + (size_t)srco[j] * p.Cout + cch));
@@ -508,7 +508,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < passes; ++j) {
                         if (!((vmask >> j) & 1u) || !ch_ok) continue;
-                        const float4 xv = (p.dbg & (8 | 64)) ? sc4 : pre[j];
+                        const float4 xv = (MG_DBGV(p) & (8 | 64)) ? sc4 : pre[j];
                         const float4 gs = make_float4(g14.x + av[j].x, g14.y + av[j].y, g14.z + av[j].z, g14.w + av[j].w);
                         if (has_aux) *reinterpret_cast<float4*>(p.aux + (size_t)pixo[j] * p.Cout + cch) = gs;
                         av[j] = make_float4(fmaf(xv.x, sc4.x, sh4.x) * gs.x, fmaf(xv.y, sc4.y, sh4.y) * gs.y,
@@ -566,7 +566,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                         *op = make_float4(y[0], y[1], y[2], y[3]);
                     }
-                    if (has_hi && !((p.dbg & (8 | 32)) && y[0] != 12345.f)) {
+                    if (has_hi && !((MG_DBGV(p) & (8 | 32)) && y[0] != 12345.f)) {
                         uint32_t hi[2], lo[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -798,16 +798,14 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.OHF = a->OHF > 0 ? a->OHF : a->OH; p.OWF = a->OWF > 0 ? a->OWF : a->OW; p.accumulate = a->accumulate;
     if (p.os != 1 && (a->epi != MG_EPI_BIAS || a->res || a->bf || a->pscale || a->pmul))
         return set_error(-8, "mg_conv_igemm: strided output supports the plain bias epilogue only");
-    static const int epi_impl_bias = getenv("MG_EPI_IMPL") ? atoi(getenv("MG_EPI_IMPL")) : 1;
-    static const int epi_impl_spade = getenv("MG_EPI_IMPL_SPADE") ? atoi(getenv("MG_EPI_IMPL_SPADE")) : epi_impl_bias;
-    const int epi_impl_env = a->epi == MG_EPI_SPADE ? epi_impl_spade : epi_impl_bias;
+    const int epi_impl_env = a->epi == MG_EPI_SPADE ? tune(TK_EPI_IMPL_SPADE) : tune(TK_EPI_IMPL);
     // epilogue chunk width: 16 channels (no register spills) unless MG_EPI_CW16=0 / MG_EPI_CW_SPADE=32 ask for 32
-    const int epi_cw16_env = getenv("MG_EPI_CW16") ? atoi(getenv("MG_EPI_CW16")) : 1;
+    const int epi_cw16_env = tune(TK_EPI_CW16);
     p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
     // epilogue chunk width (channels per TMEM->scratch->register round): 16 everywhere by default (no register spills,
     // 20 KB of scratch => one more pipeline stage at BN = 256); MG_EPI_CW16=0 / MG_EPI_CW_SPADE=32 select 32 where possible.
     const int span_epi = a->epi == MG_EPI_SPADE ? (BN >> 2) : (BN >> 1);
-    const int cw_spade = getenv("MG_EPI_CW_SPADE") ? atoi(getenv("MG_EPI_CW_SPADE")) : 16;
+    const int cw_spade = tune(TK_CW_SPADE);
     int cw = (span_epi % 32 == 0 && !p.epi_cw16) ? 32 : 16;
     if (a->epi == MG_EPI_SPADE) cw = (cw_spade == 32 && span_epi % 32 == 0) ? 32 : 16;
     const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * (cw + 4) * 4 : 0;
@@ -815,17 +813,16 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     // one [PW x (TH+2)] input patch per K chunk and read the 9 taps out of it through shifted UMMA descriptors.
     // MG_HALO: 0 off (default: measured no faster on B200 - these kernels are bound by the MMA operand fetch / epilogue,
     // not by L2->smem traffic, see profiles/r01_prof_conv_*.log), 1 on; MG_HALO_PW: patch pitch in pixels (10 = exact, 16 = swizzle-atom aligned rows);
-    // MG_HALO_BO: 1 = set the descriptor's matrix-base-offset field from the start address (measured on B200: WRONG results;
-    // the hardware applies the 128B swizzle on absolute shared-memory address bits, so the field must stay 0).
-    const int halo_env = getenv("MG_HALO") ? atoi(getenv("MG_HALO")) : 0;
-    const int halo_pw = getenv("MG_HALO_PW") ? atoi(getenv("MG_HALO_PW")) : 10;
-    p.bo_mode = getenv("MG_HALO_BO") ? atoi(getenv("MG_HALO_BO")) : 0;
+    // (The descriptor's matrix-base-offset field must stay 0: measured on B200, the hardware applies the 128B swizzle on
+    // absolute shared-memory address bits; deriving the field from the start address gives wrong results.)
+    const int halo_env = tune(TK_HALO);
+    const int halo_pw = tune(TK_HALO_PW);
     bool halo = halo_env && p.epi_impl == 1 && a->KH == 3 && a->KW == 3 && a->stride == 1 && p.pad_h == 1 && p.pad_w == 1 &&
                 a->OH >= 16 && a->OW >= 8 && a->H == a->OH && a->W == a->OW && (halo_pw == 10 || halo_pw == 16);
     // merged split precision: A_hi x [W_hi ; W_lo] (N = 2*BN) + A_lo x W_hi (N = BN): two MMAs per K step instead of
     // three (every tcgen05.mma costs >= ~100 cycles whatever its N, profiles/r01_mma_rate_microbench.log); the
     // accumulator is 2*BN columns wide and the epilogue adds the halves.  MG_MERGE=0 restores the 3-pass form.
-    const int merge_env = getenv("MG_MERGE") ? atoi(getenv("MG_MERGE")) : 1;
+    const int merge_env = tune(TK_MERGE);
     bool merged = false;
     // Only where the GEMM N is thin anyway (<= 128): for wider layers three N = 256 passes beat two passes over
     // twice as many N = 128 tiles (measured: 512->512 at 64^2 0.39 ms 3-pass vs 0.52 ms merged).
@@ -850,7 +847,9 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.a_fmt = a->a_fmt; p.parts = merged ? 2 : (a->split ? 3 : 1); p.kelem = kelem;
     p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
     p.acc_cols = p.merged ? 2 * BN : BN;
-    p.dbg = getenv("MG_DBG") ? atoi(getenv("MG_DBG")) : 0;
+#ifdef MG_PROBES
+    p.dbg = probe_bits();
+#endif
     const int stage_bytes = kABytes + p.acc_cols * 128;
     const int smem_avail = 227 * 1024 - 1024 - 512 - scratch_bytes;
     size_t ring_bytes = 0;
@@ -873,13 +872,14 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     } else {
         int stages = smem_avail / stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
-        static const int stages_cap = getenv("MG_STAGES") ? atoi(getenv("MG_STAGES")) : 0;
+        const int stages_cap = tune(TK_STAGES);
         if (stages_cap > 0 && stages > stages_cap) stages = stages_cap;
         p.stages = stages;
         ring_bytes = (size_t)stages * stage_bytes;
         // dual pipelines for thin N (one issuing thread cannot feed the tensor pipe below N = 256); MG_DUAL=0 disables
-        // MG_DUAL=2 (experiment) also splits N = 256 layers, whose ring is then only 2 + 2 stages deep
-        const int dual_env = getenv("MG_DUAL") ? atoi(getenv("MG_DUAL")) : 1;
+        // MG_DUAL=2 (default since round 2: parity-checked, -5 % on the forward) also splits N = 256 layers, whose ring is then
+        // only 2 + 2 stages deep; MG_DUAL=1 keeps those on one pipeline
+        const int dual_env = tune(TK_DUAL);
         const int sms = num_sms();
         const int dual_cols = dual_env >= 2 ? 256 : 128;
         if (dual_env && p.acc_cols <= dual_cols && stages >= 4 && p.num_tiles >= 2 * (a->max_ctas > 0 && a->max_ctas < sms ? a->max_ctas : sms)) {

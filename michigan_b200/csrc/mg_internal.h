@@ -14,6 +14,37 @@ int num_sms();
 int encode_tensor_map(CUtensorMap* map, void* gaddr, CUtensorMapDataType dtype, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                       const cuuint32_t* box, const cuuint32_t* estrides, CUtensorMapSwizzle swizzle);
 
+// Tuning knobs (alternative schedules that all give the same results): read ONCE from the environment at first use,
+// overridable through mg_set_tuning() (tests, A/B tools).  Nothing on the launch path calls getenv.
+enum TuneKnob {
+    TK_DUAL = 0,         // MG_DUAL: 0 one (producer, issuer) pipeline, 1 two for accumulators <= 128 columns, 2 (default) also for 256
+    TK_MERGE,            // MG_MERGE: split-precision convs with N <= 128 as two MMAs per K step (default 1)
+    TK_HALO,             // MG_HALO: halo schedule of 3x3/s1 convs (default 0)
+    TK_HALO_PW,          // MG_HALO_PW: patch pitch 10 | 16
+    TK_EPI_IMPL,         // MG_EPI_IMPL: 1 transposed epilogue (default), 0 row-per-lane reference epilogue
+    TK_EPI_IMPL_SPADE,   // MG_EPI_IMPL_SPADE (default: = MG_EPI_IMPL)
+    TK_EPI_CW16,         // MG_EPI_CW16: 16-channel epilogue chunks (default 1)
+    TK_CW_SPADE,         // MG_EPI_CW_SPADE: 16 | 32
+    TK_STAGES,           // MG_STAGES: cap on the smem ring depth (0 = none)
+    TK_WGRAD_DUAL,       // MG_WGRAD_DUAL (default 1)
+    TK_THIN_GEMM,        // MG_THIN_GEMM (default 1)
+    TK_THIN_WGRAD_LEGACY,// MG_THIN_WGRAD_LEGACY (default 0)
+    TK_COUNT
+};
+int tune(int knob);
+
+// What-if probes (skip loads / epilogue work: WRONG results, timing experiments only) and the clock64() role profile exist
+// only in a library built with -DMG_PROBES (python -m michigan_b200.build --probes -> libmichigan_sm100_probes.so);
+// the product library compiles them out.
+#ifdef MG_PROBES
+int probe_bits();   // env MG_DBG, read once
+#define MG_DBGV(p) ((p).dbg)
+#define MG_PROFV(p) ((p).prof)
+#else
+#define MG_DBGV(p) 0
+#define MG_PROFV(p) 0
+#endif
+
 inline int check_launch(const char* what) {
     count_launch();
     cudaError_t e = cudaGetLastError();

@@ -85,7 +85,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             tma_load_2d(w_s + 16384, &tmW, w_full, 64, 0);
             mbar_wait(w_full, 0);
             int it = 0;
-            const bool prof = p.prof && blockIdx.x == 0;
+            const bool prof = MG_PROFV(p) && blockIdx.x == 0;
             long long w_te = 0, w_af = 0, t_begin = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int s = it & 1;
@@ -116,7 +116,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
         const int IH = p.OH, IW = p.OW;
         const size_t row_stride = (size_t)IW * p.R * 4, img_stride = (size_t)IH * p.R * row_stride;
         int it = 0;
-        const bool prof = p.prof && blockIdx.x == 0 && r == 0;
+        const bool prof = MG_PROFV(p) && blockIdx.x == 0 && r == 0;
         long long c_gather = 0, c_wait = 0, c_store = 0, t_begin = prof ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
@@ -169,7 +169,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
         float* scr = scratch + ew * (32 * 68);
         const int q = lane & 7, psub = lane >> 3;   // 8 lanes per pixel (32 channels), 4 pixels per pass
         int it = 0;
-        const bool prof = p.prof && blockIdx.x == 0 && ew == 0 && lane == 0;
+        const bool prof = MG_PROFV(p) && blockIdx.x == 0 && ew == 0 && lane == 0;
         long long c_wait = 0, c_ld = 0, c_rest = 0, t_begin = prof ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
@@ -194,7 +194,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             // q*4..q*4+3 and 32+q*4.. (two requests of 8 x 16 B = 128 B each).
             {
                 float4* d = reinterpret_cast<float4*>(scr + lane * 68);
-                if (!(p.dbg & 2)) {
+                if (!(MG_DBGV(p) & 2)) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         d[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]), __uint_as_float(v0[4 * i + 2]), __uint_as_float(v0[4 * i + 3]));
@@ -214,7 +214,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
                     const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
                     const float4 t0v = *reinterpret_cast<const float4*>(scr + (j * 4 + psub) * 68 + c0);
                     const float4 t1v = *reinterpret_cast<const float4*>(scr + (j * 4 + psub) * 68 + c1);
-                    if (oh >= p.OH || ow >= p.OW || ((p.dbg & 1) && t0v.x != 12345.f)) continue;
+                    if (oh >= p.OH || ow >= p.OW || ((MG_DBGV(p) & 1) && t0v.x != 12345.f)) continue;
                     float y[8] = {t0v.x + b0.x, t0v.y + b0.y, t0v.z + b0.z, t0v.w + b0.w, t1v.x + b1.x, t1v.y + b1.y, t1v.z + b1.z, t1v.w + b1.w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -326,8 +326,10 @@ extern "C" int mg_conv_seg_tc(const mg_thin_args* a, void* stream_) {
     p.N = a->N; p.OH = a->OH; p.OW = a->OW; p.R = a->seg_resize > 0 ? a->seg_resize : 1;
     p.tiles_w = (a->OW + 15) / 16; p.tiles_h = (a->OH + 7) / 8; p.num_tiles = p.tiles_w * p.tiles_h * a->N;
     p.idesc = umma_idesc_16(128, 128, 2);
-    p.prof = getenv("MG_DBG") ? (atoi(getenv("MG_DBG")) & 16) : 0;
-    p.dbg = getenv("MG_DBG") ? (atoi(getenv("MG_DBG")) & 3) : 0;
+#ifdef MG_PROBES
+    p.prof = probe_bits() & 16;
+    p.dbg = probe_bits() & 3;
+#endif
     CUtensorMap tmW;
     {
         cuuint64_t dims[2] = {128, 128};

@@ -193,7 +193,7 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
     p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.m_tiles = (Cout + 127) / 128;
     p.n_tiles = Cin / BN;
-    static const int dual_env = getenv("MG_WGRAD_DUAL") ? atoi(getenv("MG_WGRAD_DUAL")) : 1;
+    const int dual_env = tune(TK_WGRAD_DUAL);
     p.issuers = (KW >= 2 && dual_env) ? 2 : 1;
     const int units = KH * p.m_tiles * p.n_tiles;
     int splits = (2 * num_sms() + units - 1) / units;

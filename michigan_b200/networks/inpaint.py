@@ -2,11 +2,9 @@
 row; reference: models/networks/generator.py:450-575, driven by Pix2PixModel.inpainting_orient,
 pix2pix_model.py:407-429).
 
-STATUS (end of round 1): the CPU oracle of this row is pinned against the live reference
-(tests/test_oracle_inpaint.py); this CUDA composition uses only kernels that are parity-green on the main path but has
-NOT been run on a GPU yet (the round's GPU budget was spent) — `Pix2PixModel` keeps refusing `--use_ig` unless
-MICHIGAN_B200_EXPERIMENTAL_IG=1.  The pure index arithmetic it relies on (dilated conv as a dense conv over the four
-parity sub-grids, ConvTranspose2d as the data gradient of a strided conv) is verified on the CPU in
+STATUS: GPU parity vs the pinned CPU oracle is green (tests/test_gpu_parity.py::test_inpaint_generator_vs_oracle,
+max-abs <= 1e-3 on the [0,1] output); the index arithmetic it relies on (dilated conv as a dense conv over the four
+parity sub-grids, ConvTranspose2d as the data gradient of a strided conv) is also verified on the CPU in
 tests/test_host_logic.py.
 
 Module structure = the reference's (same `nn.Sequential` indices), so the state-dict keys of
@@ -31,10 +29,6 @@ import torch.nn as nn
 
 from .. import ops, precision
 from .base_network import BaseNetwork
-
-
-def experimental_enabled():
-    return os.environ.get("MICHIGAN_B200_EXPERIMENTAL_IG", "0") == "1"
 
 
 # ------------------------------------------------------------------------------------------ pure index arithmetic

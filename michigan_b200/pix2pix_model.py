@@ -31,10 +31,6 @@ class Pix2PixModel(torch.nn.Module):
                 raise NotImplementedError("michigan_b200: --%s is outside the hot path (SURVEY.md §8)" % flag)
         self.netIG = None
         if getattr(opt, "use_ig", False):
-            from .networks import inpaint
-            if not inpaint.experimental_enabled():
-                raise NotImplementedError("michigan_b200: --use_ig (orientation inpainting net) is a 'next' row (SURVEY.md §8f); its "
-                                          "CUDA composition exists but is not GPU-validated yet - set MICHIGAN_B200_EXPERIMENTAL_IG=1 to try it")
             self.netIG = networks.define_IG(opt)
             self._load_inpainting_network(opt)
         self.netG = networks.define_G(opt)

@@ -22,6 +22,11 @@ def _fp32_reference():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+def _lib_mod():
+    from michigan_b200 import _lib
+    return _lib
+
+
 def _ops():
     from michigan_b200 import ops
     return ops
@@ -79,11 +84,11 @@ def test_igemm_16bit_operands(gen, N, h, Cin, Cout, k, s, p):
     ref32 = F.conv2d(x, w, b, stride=s, padding=p)
     wp3 = ops.pack_weight16(w, None, ops.BF16, split=True)
     for merge in ("1", "0"):
-        os.environ["MG_MERGE"] = merge
+        prev_knob = _lib_mod().set_tuning("MG_MERGE", int(merge))
         try:
             got = ops.conv_igemm(hi, wp3, Cout, k, k, s, p, bias=b, a_fmt=ops.BF16, x_lo=lo)
         finally:
-            os.environ.pop("MG_MERGE", None)
+            _lib_mod().set_tuning("MG_MERGE", prev_knob)
         assert rel_err(nchw(got), ref32) <= 6e-5, merge
 
 
@@ -99,7 +104,7 @@ def test_igemm_dual_pipelines(gen, fmt):
     b = torch.randn(Cout, generator=gen).to(dev)
     outs = {}
     for dual in ("1", "0"):
-        os.environ["MG_DUAL"] = dual
+        prev_knob = _lib_mod().set_tuning("MG_DUAL", int(dual))
         try:
             if fmt == "tf32":
                 xt, wt = tf32_trunc(x), tf32_trunc(w)
@@ -115,7 +120,7 @@ def test_igemm_dual_pipelines(gen, fmt):
                                             x_lo=lo, max_ctas=3)
                 tol = 6e-5
         finally:
-            os.environ.pop("MG_DUAL", None)
+            _lib_mod().set_tuning("MG_DUAL", prev_knob)
         assert rel_err(nchw(outs[dual]), ref) <= tol, dual
     assert torch.equal(outs["1"], outs["0"])   # same MMA order per output tile -> bit-identical
 
@@ -129,11 +134,11 @@ def test_igemm_halo_mode_matches_classic(gen):
     wp = ops.pack_weight(w, None, round_tf32=True)
     outs = []
     for halo in ("0", "1"):
-        os.environ["MG_HALO"] = halo
+        prev_knob = _lib_mod().set_tuning("MG_HALO", int(halo))
         try:
             outs.append(ops.conv_igemm(nhwc(x), wp, 128, 3, 3, 1, 1))
         finally:
-            os.environ.pop("MG_HALO", None)
+            _lib_mod().set_tuning("MG_HALO", prev_knob)
     ref = F.conv2d(x, w, None, padding=1)
     assert rel_err(nchw(outs[0]), ref) <= 2e-5 and rel_err(nchw(outs[1]), ref) <= 2e-5
     assert rel_err(outs[1], outs[0]) <= 2e-6
@@ -213,12 +218,9 @@ def test_tensor_core_wgrad_and_dgrad(gen, N, h, Cin, Cout, k, s, p):
     assert rel_err(nchw(dx), x.grad) <= 5e-5
 
 
-@pytest.mark.skipif(os.environ.get("MG_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="MG_DUAL=2 (dual pipelines for N = 256 layers) was timed at the end of round 1 but not yet run through a "
-                           "parity check; enable with MG_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("fmt", ["tf32", "f16", "bf3"])
-def test_igemm_dual_pipelines_n256_experimental(gen, fmt):
-    """Same as test_igemm_dual_pipelines for a 256-column accumulator (ring of 2 + 2 stages), MG_DUAL=2."""
+def test_igemm_dual_pipelines_n256(gen, fmt):
+    """Same as test_igemm_dual_pipelines for a 256-column accumulator (ring of 2 + 2 stages), MG_DUAL=2 (the default schedule)."""
     ops = _ops()
     N, h, Cin, Cout = 2, 32, 64, 256
     x = torch.randn(N, Cin, h, h, generator=gen).to(dev)
@@ -226,7 +228,7 @@ def test_igemm_dual_pipelines_n256_experimental(gen, fmt):
     b = torch.randn(Cout, generator=gen).to(dev)
     outs = {}
     for dual in ("2", "0"):
-        os.environ["MG_DUAL"] = dual
+        prev_knob = _lib_mod().set_tuning("MG_DUAL", int(dual))
         try:
             if fmt == "tf32":
                 xt, wt = tf32_trunc(x), tf32_trunc(w)
@@ -244,6 +246,6 @@ def test_igemm_dual_pipelines_n256_experimental(gen, fmt):
                 outs[dual] = ops.conv_igemm(hi, ops.pack_weight16(w, None, ops.BF16, split=True), Cout, 3, 3, 1, 1, bias=b, a_fmt=ops.BF16,
                                             x_lo=lo, max_ctas=3)
         finally:
-            os.environ.pop("MG_DUAL", None)
+            _lib_mod().set_tuning("MG_DUAL", prev_knob)
         assert rel_err(nchw(outs[dual]), ref) <= tol, dual
     assert torch.equal(outs["2"], outs["0"])

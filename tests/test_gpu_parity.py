@@ -311,10 +311,7 @@ def test_train_iteration_losses_and_grads_vs_golden():
     opt_D.step()
 
 
-@pytest.mark.skipif(os.environ.get("MICHIGAN_B200_EXPERIMENTAL_IG", "0") != "1",
-                    reason="row a16 (next): the InpaintGenerator CUDA composition has not been validated on a GPU yet; "
-                           "run with MICHIGAN_B200_EXPERIMENTAL_IG=1")
-def test_inpaint_generator_vs_oracle_experimental():
+def test_inpaint_generator_vs_oracle():
     """InpaintGenerator (generator.py:490-575) composed from the main path's kernels vs the CPU oracle on identical
     deterministic weights; output in [0, 1], tolerance 1e-3 max-abs like the generator image."""
     from michigan_b200.networks.inpaint import InpaintGenerator
