@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 1
+#define MG_ABI_VERSION 2
 
 int mg_version(void);
 const char* mg_last_error(void);
@@ -165,10 +165,12 @@ int mg_conv_to1(const float* x, const float* w_oihw, const float* bias, float* o
  * batchnorm.py:65-68).  sums: [2*C] doubles (sum, sum of squares), accumulated (caller zeroes).   */
 int mg_bn_stats(const float* x, long long P, int C, double* sums, void* stream);
 /* mean/var from (all-reduced) sums over `count` values -> nscale = rstd, nshift = -mean*rstd;
- * running_mean/var momentum update with unbiased variance of `count_unbiased` samples
- * (pass null to skip).  clamp_mode 0: 1/sqrt(var+eps) (batchnorm.py:65-68); 1: clamp(var,eps)^-0.5
- * (batchnorm.py:145). */
-int mg_bn_finalize(const double* sums, int C, double count, double count_unbiased, float eps, float momentum,
+ * count <= 0: the sample count is read from sums[2*C] (the per-rank counts all-reduced together with the sums,
+ * batchnorm.py:119 `sum_size`), so no host value depends on the other ranks' shard sizes.
+ * running_mean/var momentum update with the unbiased variance of count*unbiased_mult samples (unbiased_mult =
+ * 4^s when the normalised tensor is the 2^s nearest-upsampled view of x; pass null to skip).
+ * clamp_mode 0: 1/sqrt(var+eps) (batchnorm.py:65-68); 1: clamp(var,eps)^-0.5 (batchnorm.py:145). */
+int mg_bn_finalize(const double* sums, int C, double count, double unbiased_mult, float eps, float momentum,
                    int clamp_mode, float* nscale, float* nshift, float* running_mean, float* running_var,
                    float* mean_out, float* var_out, void* stream);
 /* eval mode: nscale/nshift from running stats. */
@@ -254,7 +256,8 @@ int mg_unpack_wgrad(const float* dw_packed, float* dw_oihw, int O, int I, int KH
 int mg_spade_bwd(const float* dh, const float* h, const float* g1, const float* x, int x_shift, int N, int H, int W, int C,
                  const float* nscale, const float* nshift, int act, int BN, float* dgb, float* dxhat, double* sums, void* stream);
 /* dx[N,hs,ws,C] (+)= nscale * sum over the 2^x_shift x 2^x_shift children of (g - m1 - xhat*m2), m = sums/count
- * (batch-norm backward through a folded nearest upsample); sums == null: plain child sum (upsample backward). */
+ * (batch-norm backward through a folded nearest upsample); count <= 0: read from sums[2*C] as in mg_bn_finalize;
+ * sums == null: plain child sum (upsample backward). */
 int mg_bn_bwd_apply(const float* g, const float* x, int x_shift, int N, int hs, int ws, int C, const float* nscale,
                     const float* nshift, const double* sums, double count, float* dx, int accumulate, void* stream);
 /* background blend backward (generator.py:186): dy = dout*(1-back), dbf (+)= dout*(1-hair). */
@@ -291,6 +294,24 @@ int mg_unpack_wgrad_gb(const float* dw_packed, float* dwg, float* dwb, int C, in
 /* [N,H,W,CinP] (CinP 4|8; H,W = size after the optional nearest down-sampling by seg_resize) -> TF32-rounded
  * [N,H+2p,W+2p,32] with zero channel padding and reflection padding p: operand of mg_conv_wgrad for the thin convs. */
 int mg_pad_channels32(const float* in, float* out, int N, int H, int W, int CinP, int seg_resize, int reflect_pad, void* stream);
+
+/* ---- data-parallel exchange over NVLink peer memory --------------------------------------------------------
+ * One-shot all-reduce (sum, in place) of a small fp64 vector: replaces the SyncBN master/slave message passing of
+ * sync_batchnorm/comm.py:49-133 + batchnorm.py:105-126 (ReduceAddCoalesced / Broadcast of [sum | sum of squares]).
+ *   data      : [n] doubles on this rank's device, n <= mg_peer_max_elems(); holds the all-rank sum afterwards
+ *               (same additions in the same order on every rank => bit-identical results everywhere)
+ *   peer_bufs : HOST array of `world` device pointers, entry r = rank r's exchange buffer mapped into this
+ *               process (symmetric memory / CUDA IPC), each mg_peer_buffer_bytes(world) bytes, zero-initialised
+ *               once; entry `rank` is the local buffer
+ *   seq       : 1, 2, 3, ... the same sequence on every rank (one number per exchange)
+ *   set_tail  : != 0 -> data[n-1] is replaced by `tail` before the exchange (the per-rank sample count that
+ *               travels with the BN sums, batchnorm.py:119 `sum_size`)
+ *   status_dev: device int, set to 1 if a peer's vector did not arrive within ~4 s (no hang)
+ * One CTA; enqueued on `stream`; no host synchronisation. */
+long long mg_peer_buffer_bytes(int world);
+int mg_peer_max_elems(void);
+int mg_peer_allreduce_f64(double* data, int n, const void* const* peer_bufs, int world, int rank, unsigned long long seq,
+                          int set_tail, double tail, int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

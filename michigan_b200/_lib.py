@@ -109,6 +109,9 @@ SIGNATURES = {
     "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_peer_buffer_bytes": [_i],
+    "mg_peer_max_elems": [],
+    "mg_peer_allreduce_f64": [_p, _i, _p, _i, _i, C.c_ulonglong, _i, _d, _p, _p],
 }
 
 _lib = None
@@ -134,6 +137,7 @@ def load():
         fn.restype = C.c_int
     lib.mg_last_error.restype = C.c_char_p
     lib.mg_launch_count.restype = C.c_longlong
+    lib.mg_peer_buffer_bytes.restype = C.c_longlong
     _lib = lib
     return lib
 

@@ -549,11 +549,15 @@ chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __res
     }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, double count_u, float eps,
+// count <= 0: the sample count is the (all-reduced) element sums[2*C] - the per-replica sum_size summed over ranks
+// (batchnorm.py:119), so uneven shards stay exact; unb_mult = 4^s for a folded 2^s nearest upsample.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, double unb_mult, float eps,
                                    float momentum, int clamp_mode, float* nscale, float* nshift, float* rmean,
                                    float* rvar, float* mean_out, float* var_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    if (count <= 0.0) count = sums[2 * C];
+    const double count_u = count * unb_mult;
     const double mean = sums[c] / count;
     double var = sums[C + c] / count - mean * mean;
     if (var < 0) var = 0;
@@ -1004,11 +1008,12 @@ extern "C" int mg_in_stats(const float* x, int N, long long HW, int C, double* s
     if (!x || !sums) return set_error(-1, "mg_in_stats: null pointer");
     return launch_stats(x, N, HW, C, sums, ST(stream));
 }
-extern "C" int mg_bn_finalize(const double* sums, int C, double count, double count_unbiased, float eps, float momentum,
+extern "C" int mg_bn_finalize(const double* sums, int C, double count, double unbiased_mult, float eps, float momentum,
                               int clamp_mode, float* nscale, float* nshift, float* running_mean, float* running_var,
                               float* mean_out, float* var_out, void* stream) {
     if (!sums || !nscale || !nshift) return set_error(-1, "mg_bn_finalize: null pointer");
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, ST(stream)>>>(sums, C, count, count_unbiased, eps, momentum, clamp_mode,
+    if (unbiased_mult < 1.0) return set_error(-2, "mg_bn_finalize: unbiased_mult must be >= 1");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, ST(stream)>>>(sums, C, count, unbiased_mult, eps, momentum, clamp_mode,
                                                              nscale, nshift, running_mean, running_var, mean_out, var_out);
     return check_launch("mg_bn_finalize");
 }

@@ -118,6 +118,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ g, const float* __
     const long long total = (long long)N * hs * ws * G;
     const int f = 1 << xs;
     const int w = ws << xs, h = hs << xs;
+    if (sums && inv_count <= 0.0) inv_count = 1.0 / sums[2 * C];   // all-reduced sample count (see bn_finalize_kernel)
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int g0 = idx % G;
@@ -884,7 +885,7 @@ extern "C" int mg_bn_bwd_apply(const float* g, const float* x, int x_shift, int 
     if (!g || !dx) return set_error(-1, "mg_bn_bwd_apply: null pointer");
     if (sums && (!x || !nscale || !nshift)) return set_error(-2, "mg_bn_bwd_apply: sums need x/nscale/nshift");
     bn_bwd_apply_kernel<<<ew_grid_b((long long)N * hs * ws * (C / 4)), 256, 0, ST(stream)>>>(g, x, x_shift, N, hs, ws, C, nscale, nshift,
-                                                                                            sums, sums ? 1.0 / count : 0.0, dx, accumulate);
+                                                                                            sums, (sums && count > 0.0) ? 1.0 / count : 0.0, dx, accumulate);
     return check_launch("mg_bn_bwd_apply");
 }
 extern "C" int mg_blend_bwd(const float* dout, const float* hair, const float* back, int N, int H, int W, int C, int mask_stride,

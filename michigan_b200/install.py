@@ -12,12 +12,18 @@ import os
 import sys
 
 
-def install(reference_root=None):
-    """Import the reference's `models.networks` package and rebind the hot-path classes."""
+def install(reference_root=None, compat=True):
+    """Import the reference's `models.networks` package and rebind the hot-path classes; then adapt the runtime
+    around them to one process per GPU (`_patch_runtime`).  compat=True also applies the offline / modern-PyTorch
+    shims of michigan_b200.compat (none touches hot-path arithmetic)."""
     if reference_root:
         reference_root = os.path.abspath(reference_root)
         if reference_root not in sys.path:
             sys.path.insert(0, reference_root)
+    if compat:
+        from . import compat as _compat
+        _compat.stub_optional_imports()
+        _compat.patch_adam_betas()
     from . import networks as mine
     gen = importlib.import_module("models.networks.generator")
     dis = importlib.import_module("models.networks.discriminator")
@@ -53,4 +59,44 @@ def install(reference_root=None):
                  "patch_replication_callback", "convert_model", "patch_sync_batchnorm"):
         setattr(sbn, name, getattr(mine.sync_batchnorm, name))
     pkg.SPADEBGenerator, pkg.MultiscaleDiscriminator, pkg.NLayerDiscriminator = G, MSD, NLD
+    if getattr(gen, "InpaintGenerator", None) is not None:
+        IG = both(mine.InpaintGenerator)
+        gen.InpaintGenerator = IG
+        pkg.InpaintGenerator = IG
+    if compat:
+        _compat.patch_style_content_loss(pkg)
+    _patch_runtime()
     return mine
+
+
+def _patch_runtime():
+    """What changes around the networks under one process per GPU (nothing in the reference's files is edited):
+
+      * `util.save_network` (util/util.py:195-200) -> michigan_b200.checkpoint.save_network: rank 0 only, atomic rename,
+        barrier, no round trip of the whole network through the CPU;
+      * `Pix2PixModel.compute_generator_loss` (pix2pix_model.py:257-365): the discriminator's parameters do not require
+        grad while the GENERATOR's loss is back-propagated - the reference computes those gradients and throws them
+        away (optimizer_D.zero_grad() runs before they could be used, pix2pix_trainer.py:62-69), here they are not
+        computed (and not all-reduced) at all.  Gradient averaging itself needs no hook: it happens inside backward()
+        (networks/sync_batchnorm.GradReducer), so the unchanged Pix2PixTrainer is data-parallel as is."""
+    from . import checkpoint
+    util_mod = importlib.import_module("util.util")
+    util_mod.save_network = checkpoint.save_network
+    pm = importlib.import_module("models.pix2pix_model")
+    cls = pm.Pix2PixModel
+    if not getattr(cls, "_mg_patched", False):
+        orig = cls.compute_generator_loss
+
+        def compute_generator_loss(self, *a, **k):
+            netD = getattr(self, "netD", None)
+            flags = [(p, p.requires_grad) for p in netD.parameters()] if netD is not None else []
+            for p, _ in flags:
+                p.requires_grad_(False)
+            try:
+                return orig(self, *a, **k)
+            finally:
+                for p, r in flags:
+                    p.requires_grad_(r)
+
+        cls.compute_generator_loss = compute_generator_loss
+        cls._mg_patched = True

@@ -9,6 +9,8 @@ into the consumers' loads):
     h_k     = act(x_hat*(1+gamma)+beta)         tcgen05 implicit GEMM (K=9*128, N=2C) + SPADE epilogue
     conv_0 / conv_1 / conv_s                    tcgen05 implicit GEMM + bias / residual / blend epilogue
 """
+from types import SimpleNamespace
+
 import torch
 import torch.nn as nn
 import torch.nn.utils.spectral_norm as spectral_norm
@@ -76,9 +78,12 @@ class SPADEResnetBlock(nn.Module):
         return wsh, sp.mlp_shared[0].bias.detach(), wgb, g1, sp.mlp_beta.bias.detach()
 
     # ------------------------------------------------------------------ forward
-    def forward_nhwc(self, x, x_shift, seg4, inv_sigma_of, blend=None):
+    def forward_nhwc(self, x, x_shift, seg4, inv_sigma_of, blend=None, save=None):
         """x: [N, h>>x_shift, w>>x_shift, fin] NHWC; seg4: [N,Hs,Ws,4]; returns [N,h,w,fout].
-        blend=(bf, hair, back, mask_stride) applies generator.py:186's background blend in the epilogue."""
+        blend=(bf, hair, back, mask_stride) applies generator.py:186's background blend in the epilogue.
+        save: a namespace to fill when the hand-written backward will run (autograd.block_bwd).  The arithmetic of the
+        forward is the SAME in both modes (same operand formats, same kernels): training additionally keeps, per SPADE, the
+        fp32 value of h = act(SPADE(x)) (operand of the weight-gradient GEMM) and 1 + gamma."""
         N, hs, ws, fin = x.shape
         h, w = hs << x_shift, ws << x_shift
         R = seg4.shape[1] // h
@@ -89,6 +94,8 @@ class SPADEResnetBlock(nn.Module):
             ns0, nh0, _, _ = self.norm_0.param_free_norm.scale_shift(x, x_shift, extra)
             nss, nhs = ns0, nh0
         else:
+            if save is not None:
+                raise RuntimeError("michigan_b200: the backward pass is implemented for train-mode batch statistics")
             ns0, nh0 = self.norm_0.param_free_norm.scale_shift(x)
             if self.learned_shortcut:
                 nss, nhs = self.norm_s.param_free_norm.scale_shift(x)
@@ -96,29 +103,47 @@ class SPADEResnetBlock(nn.Module):
         gfmt, gsplit = precision.gb_policy(h)
 
         def spade_act(name, src, shift, nscale, nshift, act):
-            """-> tensor-core operand (fmt, hi, lo) holding act(SPADE(src)) for the consumer conv."""
+            """-> (tensor-core operand (fmt, hi, lo) holding act(SPADE(src)) for the consumer conv, saved state | None)."""
             cfmt = precision.conv_fmt(src.shape[-1])
-            wsh, bsh, wgb, g1, bb = self._spade_pack(name, gfmt, gsplit)
+            wsh, bsh, wgb, g1b, bb = self._spade_pack(name, gfmt, gsplit)
             kw_a, get_a = precision.out_spec(gfmt, gsplit)
             actv = get_a(ops.mlp_shared(seg4, wsh, bsh, seg_resize=R, act=ops.ACT_RELU, out_hw=(h, w), **kw_a))
             c = src.shape[-1]
-            kw_h, get_h = precision.out_spec(cfmt, cfmt == ops.BF16)
-            return get_h(precision.conv(actv, wgb, c, 3, 3, 1, 1, act=act, spade=(src, shift, nscale, nshift, g1, bb), **kw_h))
+            sp_args = (src, shift, nscale, nshift, g1b, bb)
+            if save is None:
+                kw_h, get_h = precision.out_spec(cfmt, cfmt == ops.BF16)
+                return get_h(precision.conv(actv, wgb, c, 3, 3, 1, 1, act=act, spade=sp_args, **kw_h)), None
+            g1 = torch.empty((N, h, w, c), device=src.device, dtype=torch.float32)
+            if cfmt == ops.TF32:
+                h32 = precision.conv(actv, wgb, c, 3, 3, 1, 1, act=act, spade=sp_args, round_out=True, aux=g1)
+                operand = (ops.TF32, h32, None)
+            else:
+                h32, hi, lo = precision.conv(actv, wgb, c, 3, 3, 1, 1, act=act, spade=sp_args, out16=(cfmt, True), aux=g1)
+                operand = (cfmt, hi, lo)
+            S = SimpleNamespace(sp=getattr(self, name), src=src, shift=shift, ns=nscale, nh=nshift, act=act, g1=g1, h=h32,
+                                wsh=wsh, R=R, hw=(h, w))
+            return operand, S
 
+        if save is not None:
+            save.x, save.xs, save.blend, save.hw = x, x_shift, blend, (h, w)
         if self.learned_shortcut:
-            hs_ = spade_act("norm_s", x, x_shift, nss, nhs, ops.ACT_NONE)
+            hs_, sps = spade_act("norm_s", x, x_shift, nss, nhs, ops.ACT_NONE)
             x_s = precision.conv(hs_, self._conv_pack("conv_s", inv_sigma_of), self.fout, 1, 1, 1, 0)
             res, res_shift = x_s, 0
             del hs_
+            if save is not None:
+                save.sps = sps
         else:
             res, res_shift = x, x_shift
-        h0 = spade_act("norm_0", x, x_shift, ns0, nh0, ops.ACT_LRELU)
+        h0, sp0 = spade_act("norm_0", x, x_shift, ns0, nh0, ops.ACT_LRELU)
         dx = precision.conv(h0, self._conv_pack("conv_0", inv_sigma_of), self.fmiddle, 3, 3, 1, 1, bias=self.conv_0.bias.detach())
         del h0
         ns1, nh1 = self.norm_1.param_free_norm.scale_shift(dx)[:2]
-        h1 = spade_act("norm_1", dx, 0, ns1, nh1, ops.ACT_LRELU)
+        h1, sp1 = spade_act("norm_1", dx, 0, ns1, nh1, ops.ACT_LRELU)
         out = precision.conv(h1, self._conv_pack("conv_1", inv_sigma_of), self.fout, 3, 3, 1, 1, bias=self.conv_1.bias.detach(),
                              res=res, res_shift=res_shift, blend=blend)
+        if save is not None:
+            save.sp0, save.sp1, save.dx = sp0, sp1, dx
         return out
 
     def forward(self, x, seg):

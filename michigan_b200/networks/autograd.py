@@ -1,6 +1,7 @@
 """Training path: hand-written backward passes wired into torch.autograd as two Functions
-(generator, multiscale discriminator).  Forward = the same kernels as inference with fp32-stored
-TF32 operands (so that the saved activations are directly the operands of the gradient GEMMs);
+(generator, multiscale discriminator).  Forward = the networks' ONE forward implementation (`SPADEBGenerator.run`,
+`MultiscaleDiscriminator.run`) in "save" mode: the same kernels and operand formats as inference (precision.py), which
+additionally keep the fp32 value of every tensor the gradient GEMMs need (read as TF32 by the wgrad / dgrad kernels);
 backward = explicit reverse pass over the saved per-block state:
 
     conv  : dW = mg_conv_wgrad (tcgen05, MN-major, split-K);  dX = mg_conv_igemm on dY with flipped sub-kernels
@@ -15,7 +16,7 @@ from types import SimpleNamespace
 import torch
 
 from .. import ops
-from .sync_batchnorm import _world, allreduce_sums
+from .sync_batchnorm import allreduce_sums
 
 _RELU, _LRELU, _NONE = ops.ACT_RELU, ops.ACT_LRELU, ops.ACT_NONE
 
@@ -67,11 +68,6 @@ def _conv_weight(conv, inv_of):
     return conv.weight, None, False
 
 
-def _pack(conv, inv_of):
-    w, isg, _ = _conv_weight(conv, inv_of)
-    return ops.pack_weight(w.detach(), isg, True)
-
-
 def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_bias=True, dz_for_bias=None):
     """Weight (+bias) gradients of an implicit-GEMM conv; dy: [N,OH,OW,Cout], a_operand: its fp32 input."""
     w, isg, is_sn = _conv_weight(conv, inv_of)
@@ -85,18 +81,6 @@ def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_
 
 
 # =============================================================================================== SPADE + conv
-def _spade_fwd(blk, name, src, shift, ns, nh, act, seg4, R, hw):
-    sp = getattr(blk, name)
-    wsh = ops.pack_mlp_shared(sp.mlp_shared[0].weight.detach())
-    actv = ops.mlp_shared(seg4, wsh, sp.mlp_shared[0].bias.detach(), seg_resize=R, act=_RELU, round_out=True, out_hw=hw)
-    c = src.shape[-1]
-    g1 = torch.empty((src.shape[0], hw[0], hw[1], c), device=src.device, dtype=torch.float32)
-    wgb = ops.pack_weight_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach())
-    h = ops.conv_igemm(actv, wgb, c, 3, 3, 1, 1, act=act, round_out=True,
-                       spade=(src, shift, ns, nh, (sp.mlp_gamma.bias.detach() + 1.0).contiguous(), sp.mlp_beta.bias.detach()), aux=g1)
-    return SimpleNamespace(sp=sp, src=src, shift=shift, ns=ns, nh=nh, act=act, g1=g1, h=h, wsh=wsh, R=R, hw=hw)
-
-
 def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     """Backward of conv(act(SPADE(src))) given dy; returns (dxhat, sums) for the BN backward of `src`."""
     _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad)
@@ -130,31 +114,10 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
         dwt = ops.thin_wgrad(seg4, da, 3, 3, 1, 1, seg_resize=S.R, in_hw=S.hw)
     G.add(sp.mlp_shared[0].weight, _thin_wt_to_oihw(dwt, 3, 3, 4))
     G.add(sp.mlp_shared[0].bias, ops.chan_sum(da))
-    return dxhat, allreduce_sums(sums)
+    return dxhat, sums, allreduce_sums(sums, dxhat.numel() // c)
 
 
 # =============================================================================================== SPADEResnetBlock
-def block_fwd(blk, x, xs, seg4, inv_of, blend):
-    N, hs, ws, fin = x.shape
-    h, w = hs << xs, ws << xs
-    R = seg4.shape[1] // h
-    extra = (blk.norm_s.param_free_norm,) if blk.learned_shortcut else ()
-    ns0, nh0 = blk.norm_0.param_free_norm.scale_shift(x, xs, extra)[:2]
-    S = SimpleNamespace(x=x, xs=xs, blend=blend, hw=(h, w), count0=N * h * w * _world())
-    if blk.learned_shortcut:
-        S.sps = _spade_fwd(blk, "norm_s", x, xs, ns0, nh0, _NONE, seg4, R, (h, w))
-        x_s = ops.conv_igemm(S.sps.h, _pack(blk.conv_s, inv_of), blk.fout, 1, 1, 1, 0)
-        res, rshift = x_s, 0
-    else:
-        res, rshift = x, xs
-    S.sp0 = _spade_fwd(blk, "norm_0", x, xs, ns0, nh0, _LRELU, seg4, R, (h, w))
-    S.dx = ops.conv_igemm(S.sp0.h, _pack(blk.conv_0, inv_of), blk.fmiddle, 3, 3, 1, 1, bias=blk.conv_0.bias.detach())
-    ns1, nh1 = blk.norm_1.param_free_norm.scale_shift(S.dx)[:2]
-    S.sp1 = _spade_fwd(blk, "norm_1", S.dx, 0, ns1, nh1, _LRELU, seg4, R, (h, w))
-    out = ops.conv_igemm(S.sp1.h, _pack(blk.conv_1, inv_of), blk.fout, 3, 3, 1, 1, bias=blk.conv_1.bias.detach(), res=res, res_shift=rshift, blend=blend)
-    return out, S
-
-
 def block_bwd(G, blk, S, dout, seg4, inv_of):
     """-> (dx wrt the block input (pre-upsample), dbf wrt the blended background feature or None)."""
     seg_cache = {}
@@ -164,51 +127,22 @@ def block_bwd(G, blk, S, dout, seg4, inv_of):
         dy, dbf = ops.blend_bwd(dout, hair, back, ms)
     else:
         dy = dout
-    N = dy.shape[0]
-    h, w = S.hw
-    dxhat1, sums1 = _spade_conv_bwd(G, blk, S.sp1, blk.conv_1, inv_of, dy, 3, 1, seg4, seg_cache)
-    ddx = ops.bn_bwd_apply(dxhat1, S.dx, 0, S.sp1.ns, S.sp1.nh, sums1, N * h * w * _world())
+    dxhat1, sums1, cnt1 = _spade_conv_bwd(G, blk, S.sp1, blk.conv_1, inv_of, dy, 3, 1, seg4, seg_cache)
+    ddx = ops.bn_bwd_apply(dxhat1, S.dx, 0, S.sp1.ns, S.sp1.nh, sums1, cnt1)
     del dxhat1
-    dxhat0, sums0 = _spade_conv_bwd(G, blk, S.sp0, blk.conv_0, inv_of, ddx, 3, 1, seg4, seg_cache)
+    dxhat0, sums0, cnt0 = _spade_conv_bwd(G, blk, S.sp0, blk.conv_0, inv_of, ddx, 3, 1, seg4, seg_cache)
     del ddx
-    dx = ops.bn_bwd_apply(dxhat0, S.x, S.xs, S.sp0.ns, S.sp0.nh, sums0, S.count0)
+    dx = ops.bn_bwd_apply(dxhat0, S.x, S.xs, S.sp0.ns, S.sp0.nh, sums0, cnt0)
     del dxhat0
     if blk.learned_shortcut:
-        dxhat_s, sums_s = _spade_conv_bwd(G, blk, S.sps, blk.conv_s, inv_of, dy, 1, 0, seg4, seg_cache)
-        ops.bn_bwd_apply(dxhat_s, S.x, S.xs, S.sps.ns, S.sps.nh, sums_s, S.count0, dx=dx)
+        dxhat_s, sums_s, cnt_s = _spade_conv_bwd(G, blk, S.sps, blk.conv_s, inv_of, dy, 1, 0, seg4, seg_cache)
+        ops.bn_bwd_apply(dxhat_s, S.x, S.xs, S.sps.ns, S.sps.nh, sums_s, cnt_s, dx=dx)
     else:
         ops.bn_bwd_apply(dy, S.x, S.xs, None, None, None, 1, dx=dx)   # identity shortcut through the upsample
     return dx, dbf
 
 
 # =============================================================================================== encoders
-def fc_fwd(fc, image_ref, label_ref0, label_tag0):
-    N, _, H, W = image_ref.shape
-    mref = label_ref0.reshape(N, H, W).contiguous()
-    mtag = label_tag0.reshape(N, H, W).contiguous()
-    S = SimpleNamespace(mref=mref, mtag=mtag, layers=[])
-    S.x0 = ops.nchw_to_nhwc(image_ref.contiguous(), 4, pmul=mref)
-    ratio, upd = ops.partial_mask(mref, 3, 2, 1)
-    S.wt1 = ops.pack_weight_thin(fc.layer1.weight.detach(), 4)
-    y = ops.conv_thin(S.x0, S.wt1, fc.layer1.bias.detach(), fc.layer1.out_channels, 3, 3, 2, 1, pscale=ratio, pmul=upd)
-    S.l1 = SimpleNamespace(ratio=ratio, upd=upd, y=y)
-    prev_upd = upd
-    for i in range(2, 6):
-        a, ss = ops.instance_norm_act_fwd(y, _LRELU, 1e-5, round_out=True, pmul=prev_upd)
-        ratio, upd = ops.partial_mask(prev_upd, 3, 2, 1)
-        layer = getattr(fc, "layer%d" % i)
-        y_next = ops.conv_igemm(a, ops.pack_weight(layer.weight.detach(), None, True), layer.out_channels, 3, 3, 2, 1,
-                                bias=layer.bias.detach(), pscale=ratio, pmul=upd)
-        S.layers.append(SimpleNamespace(layer=layer, a=a, ss=ss, y_in=y, pm_in=prev_upd, ratio=ratio, upd=upd))
-        y, prev_upd = y_next, upd
-    a6, ss6 = ops.instance_norm_act_fwd(y, _LRELU, 1e-5)
-    S.y5, S.ss6 = y, ss6
-    m = ops.masked_mean_bcast(a6, mref, mtag)
-    S.mhw = (m.shape[1], m.shape[2])
-    out = ops.resize_bilinear(m, fc.sh, fc.sw) if fc.sh != m.shape[1] else m
-    return out, S
-
-
 def fc_bwd(G, fc, S, dout):
     d = ops.resize_bilinear_bwd(dout, S.mhw) if (dout.shape[1], dout.shape[2]) != S.mhw else dout
     d = ops.masked_mean_bcast_bwd(d, S.mref, S.mtag)
@@ -224,26 +158,6 @@ def fc_bwd(G, fc, S, dout):
     dwt1 = (ops.thin_wgrad_tc(ops.pad_channels32(S.x0), dz, 3, 3, 2, 1, 4) if ops.thin_wgrad_tc_enabled()
             else ops.thin_wgrad(S.x0, dz, 3, 3, 2, 1))
     G.add(fc.layer1.weight, _thin_wt_to_oihw(dwt1, 3, 3, 3))
-
-
-def bg_fwd(bg, image, mask, noise):
-    back = bg.back_mask(mask)
-    inp = ops.nchw_to_nhwc(noise.contiguous(), 4) if bg.opt.random_noise_background else \
-        ops.prep_bginput(image.contiguous(), noise.contiguous(), back)
-    S = SimpleNamespace(inp=inp, layers=[])
-    S.wt1 = ops.pack_weight_thin(bg.conv1.conv.weight.detach(), 4)
-    x = ops.conv_thin(inp, S.wt1, bg.conv1.conv.bias.detach(), bg.ngf, 7, 7, 1, 3, pad_mode=1, act=_RELU)
-    S.x0 = x
-    feats = [x]
-    for name in ("layer1", "layer2", "layer3"):
-        blk = getattr(bg, name)
-        xp = ops.reflect_pad(x, 1, round_tf32=True)
-        y = ops.conv_igemm(xp, ops.pack_weight(blk.conv.weight.detach(), None, True), blk.conv.out_channels, 4, 4, 2, 0,
-                           bias=blk.conv.bias.detach(), act=_RELU)
-        S.layers.append(SimpleNamespace(blk=blk, xp=xp, y=y))
-        x = y
-        feats.append(y)
-    return feats[::-1], back, S
 
 
 def bg_bwd(G, bg, S, dfeats):
@@ -268,23 +182,10 @@ def bg_bwd(G, bg, S, dfeats):
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, netG, input_ref, orient_mask, image_ref, input_tag, noise, image_tag, *params):
-        opt = netG.opt
-        input_tag = input_tag.contiguous()
-        seg4 = ops.prep_seg(input_tag, orient_mask.contiguous())
-        x, Sfc = fc_fwd(netG.fc, image_ref, input_ref[:, 1:2], input_tag[:, 1:2])
-        feats, back, Sbg = bg_fwd(netG.backgroud_enc, image_tag, input_tag, noise)
-        hair = input_tag[:, 1].contiguous()
-        snb = netG.spectral_batch()
-        inv = snb.run(netG.training)
-        inv_of = {c: inv[i:i + 1].clone() for i, c in enumerate(snb.convs)}
-        saved = []
-        x, S = block_fwd(netG.head_0, x, 0, seg4, inv_of, None); saved.append(S)
-        x, S = block_fwd(netG.G_middle_0, x, 1, seg4, inv_of, None); saved.append(S)
-        x, S = block_fwd(netG.G_middle_1, x, 1, seg4, inv_of, None); saved.append(S)
-        for i in range(4):
-            x, S = block_fwd(getattr(netG, "up_%d" % i), x, 1, seg4, inv_of, (feats[i], hair, back, 8 >> i)); saved.append(S)
-        out = ops.conv_img(x, netG.conv_img.weight.detach(), netG.conv_img.bias.detach())
-        ctx.netG, ctx.seg4, ctx.inv_of, ctx.saved, ctx.Sfc, ctx.Sbg, ctx.x_last, ctx.out = netG, seg4, inv_of, saved, Sfc, Sbg, x, out
+        st = SimpleNamespace()
+        out = netG.run(input_ref, orient_mask, image_ref, input_tag, noise, image_tag, st)
+        ctx.netG, ctx.seg4, ctx.inv_of, ctx.saved, ctx.Sfc, ctx.Sbg, ctx.x_last, ctx.out = \
+            netG, st.seg4, st.inv_of, st.saved, st.Sfc, st.Sbg, st.x_last, st.out
         ctx.params = params
         return out
 
@@ -292,10 +193,14 @@ class _GeneratorFn(torch.autograd.Function):
     def backward(ctx, dout):
         netG, seg4, inv_of = ctx.netG, ctx.seg4, ctx.inv_of
         G = _Grads()
+        red = getattr(netG, "_grad_reducer", None)   # data-parallel: stages are all-reduced while later stages compute
+        if red is not None:
+            red.begin(ctx.params)
         dx, dw, db = ops.conv_img_bwd(dout.contiguous(), ctx.out, ctx.x_last, netG.conv_img.weight.detach())
         G.add(netG.conv_img.weight, dw)
         G.add(netG.conv_img.bias, db)
-        names = ["head_0", "G_middle_0", "G_middle_1", "up_0", "up_1", "up_2", "up_3"]
+        names = netG._blocks
+        stage_of = netG.GRAD_STAGE_AFTER_BLOCK
         dfeats = [None] * 4
         for idx in range(6, -1, -1):
             blk = getattr(netG, names[idx])
@@ -303,11 +208,15 @@ class _GeneratorFn(torch.autograd.Function):
             ctx.saved[idx] = None
             if idx >= 3:
                 dfeats[idx - 3] = dbf
+            if red is not None and names[idx] in stage_of:
+                red.reduce_stage(stage_of[names[idx]], G.get)
         fc_bwd(G, netG.fc, ctx.Sfc, dx)
         bg_bwd(G, netG.backgroud_enc, ctx.Sbg, dfeats)
-        grads = tuple(G.get(p) for p in ctx.params)
         ctx.saved = ctx.Sfc = ctx.Sbg = None
-        return (None,) * 7 + grads
+        if red is not None:
+            red.reduce_stage(len(red.stages) - 1, G.get)
+            return (None,) * 7 + red.finish(ctx.params, G.get)
+        return (None,) * 7 + tuple(G.get(p) for p in ctx.params)
 
 
 def generator_forward_autograd(netG, input_ref, orient_mask, image_ref, input_tag, noise, image_tag):
@@ -316,26 +225,6 @@ def generator_forward_autograd(netG, input_ref, orient_mask, image_ref, input_ta
 
 
 # =============================================================================================== discriminator Function
-def _d_scale_fwd(D, x8, inv_of):
-    S = SimpleNamespace(x8=x8, layers=[])
-    conv0 = D.model0[0]
-    S.wt0 = ops.pack_weight_thin(conv0.weight.detach(), 8)
-    f = ops.conv_thin(x8, S.wt0, conv0.bias.detach(), conv0.out_channels, 4, 4, 2, D.padw, act=_LRELU, round_out=True)
-    S.f0 = f
-    outs = [f]
-    for n, conv in zip(range(1, D.n_layers), D.mid_convs()):
-        w, isg, _ = _conv_weight(conv, inv_of)
-        raw = ops.conv_igemm(f, ops.pack_weight(w.detach(), isg, True), conv.out_channels, 4, 4, D._strides[n], D.padw)
-        f_next, ss = ops.instance_norm_act_fwd(raw, _LRELU, 1e-5, round_out=True)
-        S.layers.append(SimpleNamespace(conv=conv, stride=D._strides[n], f_in=f, raw=raw, ss=ss))
-        f = f_next
-        outs.append(f)
-    last = getattr(D, "model%d" % D.n_layers)[0]
-    S.f_last, S.last = f, last
-    outs.append(ops.conv_to1(f, last.weight.detach(), last.bias.detach(), D.padw))
-    return outs, S
-
-
 def _d_scale_bwd(G, D, S, douts, inv_of, need_dimg, param_grads):
     """douts: list of NHWC grads (or None) for [f0..f3, logits]; returns dimg NCHW [B,3,H,W] or None."""
     nl = D.n_layers
@@ -378,18 +267,9 @@ def _d_scale_bwd(G, D, S, douts, inv_of, need_dimg, param_grads):
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, netD, x_nchw, *params):
-        snb = netD.spectral_batch()
-        inv = snb.run(netD.training)
-        inv_of = {cv: inv[i:i + 1].clone() for i, cv in enumerate(snb.convs)} if inv is not None else {}
-        x8 = ops.nchw_to_nhwc(x_nchw.contiguous(), 8)
-        states, flat = [], []
-        children = [D for _, D in netD.named_children()]
-        for i, D in enumerate(children):
-            outs, S = _d_scale_fwd(D, x8, inv_of)
-            states.append(S)
-            flat += [o.permute(0, 3, 1, 2) for o in outs]
-            if i + 1 < len(children):
-                x8 = ops.avgpool3s2(x8)
+        states = []
+        result, inv_of = netD.run(x_nchw, states)
+        flat = [o for outs in result for o in outs]
         ctx.netD, ctx.states, ctx.inv_of, ctx.params = netD, states, inv_of, params
         ctx.need_dimg = x_nchw.requires_grad
         ctx.param_grads = any(p.requires_grad for p in params)
@@ -403,9 +283,14 @@ class _DiscriminatorFn(torch.autograd.Function):
         children = [D for _, D in netD.named_children()]
         per = children[0].n_layers + 1
         dimg_total = None
+        red = getattr(netD, "_grad_reducer", None) if ctx.param_grads else None
+        if red is not None:
+            red.begin(ctx.params)
         for i in range(len(children) - 1, -1, -1):
             douts = [(_nhwc(g) if g is not None else None) for g in gouts[i * per:(i + 1) * per]]
             dimg = _d_scale_bwd(G, children[i], ctx.states[i], douts, ctx.inv_of, ctx.need_dimg, ctx.param_grads)
+            if red is not None:
+                red.reduce_stage(len(children) - 1 - i, G.get)   # stage order = backward order (coarsest scale first)
             if ctx.need_dimg and dimg is not None:
                 if dimg_total is None:
                     dimg_total = dimg
@@ -424,9 +309,12 @@ class _DiscriminatorFn(torch.autograd.Function):
             dx = torch.zeros(ctx.in_shape, device=gouts[0].device if gouts[0] is not None else None, dtype=torch.float32)
             if dimg_total is not None:
                 dx[:, 4:7] = dimg_total
-        grads = tuple(G.get(p) for p in ctx.params) if ctx.param_grads else (None,) * len(ctx.params)
         ctx.states = None
-        return (None, dx) + grads
+        if not ctx.param_grads:
+            return (None, dx) + (None,) * len(ctx.params)
+        if red is not None:
+            return (None, dx) + red.finish(ctx.params, G.get)
+        return (None, dx) + tuple(G.get(p) for p in ctx.params)
 
 
 def discriminator_forward_autograd(netD, x_nchw):

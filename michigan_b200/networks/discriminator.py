@@ -8,6 +8,8 @@ state-dict layout of the reference's models/networks/discriminator.py:14-120 (no
     model4      512->1 k4 s1 p2 + bias                       warp-per-pixel dot product
     downsample  avg_pool2d(3, 2, 1, count_include_pad=False) on the 8-channel NHWC input
 """
+from types import SimpleNamespace
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -66,24 +68,26 @@ class NLayerDiscriminator(BaseNetwork):
         """The (possibly spectrally-normalised) convs of model1..model{n-1}."""
         return [getattr(self, "model%d" % n)[0][0] for n in range(1, self.n_layers)]
 
-    def forward_nhwc(self, x8, inv_sigma_of):
-        """x8: [B,H,W,8] -> list of NHWC tensors (all intermediates + logits)."""
+    def forward_nhwc(self, x8, inv_sigma_of, save=None):
+        """x8: [B,H,W,8] -> list of NHWC tensors (all intermediates + logits).
+        save: namespace filled with what autograd._d_scale_bwd needs; the arithmetic is the same either way."""
         c = self._cache
         conv0 = self.model0[0]
         w0 = c.get("m0", [conv0.weight], lambda: ops.pack_weight_thin(conv0.weight.detach(), 8))
         # one-pass fp16 (or TF32): the discriminator is not under the generator's image-error bound
-        def as_operand(r, fmt):
-            """(feature fp32, operand) from a producer's return value."""
-            if fmt == ops.TF32:
-                return r, (ops.TF32, r, None)
-            return r[0], (fmt, r[1], None)
 
         def kw_for(fmt):
             return dict(round_out=True) if fmt == ops.TF32 else dict(out16=(fmt, False))
 
+        def operand(r, fmt):
+            """(feature fp32, tensor-core operand) from a producer's return value (fp32 | (fp32, hi, lo))."""
+            return (r, (ops.TF32, r, None)) if fmt == ops.TF32 else (r[0], (fmt, r[1], None))
+
         fmt = precision.gb_fmt(conv0.out_channels)
-        kw_o = kw_for(fmt)
-        x, xo = as_operand(ops.conv_thin(x8, w0, conv0.bias.detach(), conv0.out_channels, 4, 4, 2, self.padw, act=ops.ACT_LRELU, **kw_o), fmt)
+        x, xo = operand(ops.conv_thin(x8, w0, conv0.bias.detach(), conv0.out_channels, 4, 4, 2, self.padw, act=ops.ACT_LRELU,
+                                      **kw_for(fmt)), fmt)
+        if save is not None:
+            save.x8, save.wt0, save.f0, save.layers = x8, w0, x, []
         outs = [x]
         for n, conv in zip(range(1, self.n_layers), self.mid_convs()):
             if hasattr(conv, "weight_orig"):
@@ -95,10 +99,18 @@ class NLayerDiscriminator(BaseNetwork):
                 wp = c.get(("m%d" % n, fmt), [conv.weight], lambda conv=conv: ops.pack_weight16(conv.weight.detach(), None, fmt, split=False))
             raw = precision.conv(xo, wp, conv.out_channels, 4, 4, self._strides[n], self.padw)
             fmt = precision.gb_fmt(conv.out_channels)
-            x, xo = as_operand(ops.instance_norm_act(raw, ops.ACT_LRELU, 1e-5, **kw_for(fmt)), fmt)
+            f_in = x
+            if save is None:
+                x, xo = operand(ops.instance_norm_act(raw, ops.ACT_LRELU, 1e-5, **kw_for(fmt)), fmt)
+            else:
+                r = ops.instance_norm_act_fwd(raw, ops.ACT_LRELU, 1e-5, **kw_for(fmt))
+                x, xo = operand(r[0] if fmt == ops.TF32 else (r[0], r[2], r[3]), fmt)
+                save.layers.append(SimpleNamespace(conv=conv, stride=self._strides[n], f_in=f_in, raw=raw, ss=r[1]))
             outs.append(x)
         last = getattr(self, "model%d" % self.n_layers)[0]
         outs.append(ops.conv_to1(x, last.weight.detach(), last.bias.detach(), self.padw))
+        if save is not None:
+            save.f_last, save.last = x, last
         return outs
 
     def forward(self, input):
@@ -132,6 +144,10 @@ class MultiscaleDiscriminator(BaseNetwork):
             return NLayerDiscriminator(opt)
         raise ValueError("unrecognized discriminator subarchitecture %s" % opt.netD_subarch)
 
+    def grad_stages(self):
+        """Gradient all-reduce stages in backward order (autograd._DiscriminatorFn.backward: coarsest scale first)."""
+        return [list(D.parameters()) for _, D in reversed(list(self.named_children()))]
+
     def spectral_batch(self):
         if self._snb is None:
             convs = []
@@ -150,14 +166,26 @@ class MultiscaleDiscriminator(BaseNetwork):
         return self.forward_nograd(input)
 
     def forward_nograd(self, input):
+        return self.run(input, None)
+
+    def run(self, input, save):
+        """The one forward implementation (save=None: no-grad; save=list to fill with per-scale state for the backward)."""
         snb = self.spectral_batch()
         inv = snb.run(self.training)
-        inv_of = {cv: inv[i:i + 1] for i, cv in enumerate(snb.convs)} if inv is not None else {}
+        if inv is None:
+            inv_of = {}
+        else:
+            inv_of = {cv: (inv[i:i + 1].clone() if save is not None else inv[i:i + 1]) for i, cv in enumerate(snb.convs)}
         x8 = ops.nchw_to_nhwc(input.contiguous(), 8)
-        get_feats = not self.opt.no_ganFeat_loss
+        get_feats = not self.opt.no_ganFeat_loss or save is not None
         result = []
-        for _, D in self.named_children():
-            outs = [o.permute(0, 3, 1, 2) for o in D.forward_nhwc(x8, inv_of)]
+        children = [D for _, D in self.named_children()]
+        for i, D in enumerate(children):
+            S = SimpleNamespace() if save is not None else None
+            outs = [o.permute(0, 3, 1, 2) for o in D.forward_nhwc(x8, inv_of, save=S)]
             result.append(outs if get_feats else [outs[-1]])
-            x8 = ops.avgpool3s2(x8)
-        return result
+            if save is not None:
+                save.append(S)
+            if i + 1 < len(children):
+                x8 = ops.avgpool3s2(x8)
+        return (result, inv_of) if save is not None else result

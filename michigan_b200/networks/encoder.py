@@ -3,6 +3,7 @@
 (encoder.py:271-341, MaskGAN_networks.py:114-173).  Same constructors and state-dict keys; forward on
 the CUDA kernels, NHWC inside."""
 import random
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -53,29 +54,48 @@ class ImageEncoder3(BaseNetwork):
             raise NotImplementedError("michigan_b200: ngf must be a multiple of 32")
         self._cache = PackCache()
 
-    def forward_nhwc(self, image_ref, label_ref0, label_tag0):
-        """image_ref [N,3,H,W] NCHW, label_* [N,1,H,W] -> [N,sh,sw,16*ngf] NHWC."""
+    def forward_nhwc(self, image_ref, label_ref0, label_tag0, save=None):
+        """image_ref [N,3,H,W] NCHW, label_* [N,1,H,W] -> [N,sh,sw,16*ngf] NHWC.
+        save: namespace filled with what autograd.fc_bwd needs (same arithmetic either way)."""
         N, _, H, W = image_ref.shape
         mref = label_ref0.reshape(N, H, W).contiguous()
         mtag = label_tag0.reshape(N, H, W).contiguous()
         c = self._cache
         # layer 1: thin direct conv on image*mask
-        x = ops.nchw_to_nhwc(image_ref.contiguous(), 4, pmul=mref)
+        x0 = ops.nchw_to_nhwc(image_ref.contiguous(), 4, pmul=mref)
         ratio, upd = ops.partial_mask(mref, 3, 2, 1)
         w1 = c.get("l1", [self.layer1.weight], lambda: ops.pack_weight_thin(self.layer1.weight.detach(), 4))
-        x = ops.conv_thin(x, w1, self.layer1.bias.detach(), self.layer1.out_channels, 3, 3, 2, 1, pscale=ratio, pmul=upd)
+        x = ops.conv_thin(x0, w1, self.layer1.bias.detach(), self.layer1.out_channels, 3, 3, 2, 1, pscale=ratio, pmul=upd)
+        if save is not None:
+            save.mref, save.mtag, save.x0, save.wt1, save.layers = mref, mtag, x0, w1, []
+            save.l1 = SimpleNamespace(ratio=ratio, upd=upd, y=x)
         for i in range(2, 6):
             # lrelu(IN(x)) * mask as a tensor-core operand of the next partial conv (partialconv2d.py:69)
             fmt = precision.conv_fmt(x.shape[-1])
-            kw_o, get_o = precision.out_spec(fmt, fmt == ops.BF16)
-            xo = get_o(ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5, pmul=upd, **kw_o))
+            if save is None:
+                kw_o, get_o = precision.out_spec(fmt, fmt == ops.BF16)
+                xo = get_o(ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5, pmul=upd, **kw_o))
+            elif fmt == ops.TF32:
+                a32, ss = ops.instance_norm_act_fwd(x, ops.ACT_LRELU, 1e-5, round_out=True, pmul=upd)
+                xo = (ops.TF32, a32, None)
+            else:
+                a32, ss, hi, lo = ops.instance_norm_act_fwd(x, ops.ACT_LRELU, 1e-5, pmul=upd, out16=(fmt, True))
+                xo = (fmt, hi, lo)
             ratio, upd_next = ops.partial_mask(upd, 3, 2, 1)
             layer = getattr(self, "layer%d" % i)
             wp = c.get(("l%d" % i, fmt), [layer.weight], lambda layer=layer: precision.pack_conv(layer.weight.detach(), None, fmt))
-            x = precision.conv(xo, wp, layer.out_channels, 3, 3, 2, 1, bias=layer.bias.detach(), pscale=ratio, pmul=upd_next)
-            upd = upd_next
-        x = ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5)
-        out = ops.masked_mean_bcast(x, mref, mtag)
+            y = precision.conv(xo, wp, layer.out_channels, 3, 3, 2, 1, bias=layer.bias.detach(), pscale=ratio, pmul=upd_next)
+            if save is not None:
+                save.layers.append(SimpleNamespace(layer=layer, a=a32, ss=ss, y_in=x, pm_in=upd, ratio=ratio, upd=upd_next))
+            x, upd = y, upd_next
+        if save is None:
+            a6 = ops.instance_norm_act(x, ops.ACT_LRELU, 1e-5)
+        else:
+            a6, ss6 = ops.instance_norm_act_fwd(x, ops.ACT_LRELU, 1e-5)
+            save.y5, save.ss6 = x, ss6
+        out = ops.masked_mean_bcast(a6, mref, mtag)
+        if save is not None:
+            save.mhw = (out.shape[1], out.shape[2])
         if self.sh != out.shape[1]:
             out = ops.resize_bilinear(out, self.sh, self.sw)
         return out
@@ -142,8 +162,8 @@ class BackgroundEncode2(BaseNetwork):
             return ops.maxpool_mask(hair, k, invert=True)
         return mask[:, 0].contiguous()
 
-    def forward_nhwc(self, image, mask, noise):
-        """Returns ([x3,x2,x1,x0] NHWC features, back_mask [N,H,W])."""
+    def forward_nhwc(self, image, mask, noise, save=None):
+        """Returns ([x3,x2,x1,x0] NHWC features, back_mask [N,H,W]).  save: namespace for autograd.bg_bwd."""
         back = self.back_mask(mask)
         if self.opt.random_noise_background:
             inp = ops.nchw_to_nhwc(noise.contiguous(), 4)
@@ -152,6 +172,8 @@ class BackgroundEncode2(BaseNetwork):
         c = self._cache
         w1 = c.get("c1", [self.conv1.conv.weight], lambda: ops.pack_weight_thin(self.conv1.conv.weight.detach(), 4))
         x0 = ops.conv_thin(inp, w1, self.conv1.conv.bias.detach(), self.ngf, 7, 7, 1, 3, pad_mode=1, act=ops.ACT_RELU)
+        if save is not None:
+            save.inp, save.wt1, save.x0, save.layers = inp, w1, x0, []
         feats = [x0]
         x = x0
         for name in ("layer1", "layer2", "layer3"):
@@ -159,11 +181,14 @@ class BackgroundEncode2(BaseNetwork):
             fmt = precision.conv_fmt(x.shape[-1])
             wp = c.get((name, fmt), [blk.conv.weight], lambda blk=blk: precision.pack_conv(blk.conv.weight.detach(), None, fmt))
             if fmt == ops.TF32:
-                xp = (ops.TF32, ops.reflect_pad(x, 1, round_tf32=True), None)
+                xp32 = ops.reflect_pad(x, 1, round_tf32=True)
+                xp = (ops.TF32, xp32, None)
             else:
-                _, hi, lo = ops.reflect_pad(x, 1, out16=(fmt, True), want_f32=False)
+                xp32, hi, lo = ops.reflect_pad(x, 1, out16=(fmt, True), want_f32=save is not None)
                 xp = (fmt, hi, lo)
             x = precision.conv(xp, wp, blk.conv.out_channels, 4, 4, 2, 0, bias=blk.conv.bias.detach(), act=ops.ACT_RELU)
+            if save is not None:
+                save.layers.append(SimpleNamespace(blk=blk, xp=xp32, y=x))
             feats.append(x)
         return feats[::-1], back
 

@@ -6,6 +6,8 @@ written TF32-rounded by their producer; the 2x nearest upsamples (generator.py:7
 hair/background mask pyramids (generator.py:149-159, encoder.py:332-336) are never materialised -
 consumers index the low-resolution tensor / full-resolution mask directly.
 """
+from types import SimpleNamespace
+
 import torch
 
 from .. import ops
@@ -63,6 +65,17 @@ class SPADEBGenerator(BaseNetwork):
         sh = round(sw / opt.aspect_ratio)
         return sw, sh
 
+    # Gradient all-reduce stages, in the order the backward finalises them (autograd._GeneratorFn.backward): the key is the
+    # block after whose backward the stage is complete.  Sizes (ngf 64): 30 / 54 / 94 / 94 / 94 / 36 MB - the three 94 MB
+    # stages come out while only the cheap low-resolution blocks are left to compute.
+    GRAD_STAGE_AFTER_BLOCK = {"up_1": 0, "up_0": 1, "G_middle_1": 2, "G_middle_0": 3, "head_0": 4}
+
+    def grad_stages(self):
+        def ps(*mods):
+            return [p for m in mods for p in m.parameters()]
+        return [ps(self.conv_img, self.up_3, self.up_2, self.up_1), ps(self.up_0), ps(self.G_middle_1), ps(self.G_middle_0),
+                ps(self.head_0), ps(self.fc, self.backgroud_enc)]
+
     def spectral_batch(self):
         if self._snb is None:
             convs = []
@@ -82,41 +95,48 @@ class SPADEBGenerator(BaseNetwork):
         return self.forward_nograd(input, orient_mask, image_ref, input_tag, noise, image_tag)
 
     def forward_nograd(self, input, orient_mask, image_ref, input_tag, noise, image_tag):
+        return self.run(input, orient_mask, image_ref, input_tag, noise, image_tag, None)
+
+    def run(self, input, orient_mask, image_ref, input_tag, noise, image_tag, save):
+        """The one forward implementation.  save=None: inference / no-grad; save=namespace: the autograd Function's forward,
+        which keeps per-block state for the hand-written backward (networks/autograd.py) - identical arithmetic."""
         opt = self.opt
+        if opt.bf_direct_add:
+            raise NotImplementedError("michigan_b200: --bf_direct_add is not implemented")
         N, _, H, W = input_tag.shape
         input_tag = input_tag.contiguous()
         seg4 = ops.prep_seg(input_tag, orient_mask.contiguous())          # generator.py:129-142
         ins_ref = input[:, 1:2]
         ins_tag = input_tag[:, 1:2]
-        x = self.fc.forward_nhwc(image_ref, ins_ref, ins_tag)              # generator.py:117-123
-        feats, back = self.backgroud_enc.forward_nhwc(image_tag, input_tag, noise)  # generator.py:144-147
+        sv = (lambda: SimpleNamespace()) if save is not None else (lambda: None)
+        Sfc, Sbg = sv(), sv()
+        x = self.fc.forward_nhwc(image_ref, ins_ref, ins_tag, save=Sfc)              # generator.py:117-123
+        feats, back = self.backgroud_enc.forward_nhwc(image_tag, input_tag, noise, save=Sbg)  # generator.py:144-147
         hair = input_tag[:, 1].contiguous()
         snb = self.spectral_batch()
         inv = snb.run(self.training)
-        inv_of = {c: inv[i:i + 1] for i, c in enumerate(snb.convs)}
+        # training keeps private copies: the D step's no-grad forward re-runs the power iteration before this backward is gone
+        inv_of = {c: (inv[i:i + 1].clone() if save is not None else inv[i:i + 1]) for i, c in enumerate(snb.convs)}
         taps = {} if self.collect_taps else None
         if taps is not None:
             taps["fc"] = x
             for i, f in enumerate(feats):
                 taps["bg%d" % i] = f
-
-        x = self.head_0.forward_nhwc(x, 0, seg4, inv_of)
-        if taps is not None:
-            taps["head_0"] = x
-        x = self.G_middle_0.forward_nhwc(x, 1, seg4, inv_of)
-        if taps is not None:
-            taps["G_middle_0"] = x
-        x = self.G_middle_1.forward_nhwc(x, 1, seg4, inv_of)
-        if taps is not None:
-            taps["G_middle_1"] = x
-        for i in range(4):
-            blk = getattr(self, "up_%d" % i)
-            ms = 8 >> i  # hair_masks / back_masks pyramid level == stride into the full-resolution masks
-            if opt.bf_direct_add:
-                raise NotImplementedError("michigan_b200: --bf_direct_add is not implemented")
-            x = blk.forward_nhwc(x, 1, seg4, inv_of, blend=(feats[i], hair, back, ms))
+        saved = []
+        for idx, name in enumerate(self._blocks):
+            blk = getattr(self, name)
+            S = sv()
+            if idx < 3:
+                x = blk.forward_nhwc(x, 0 if idx == 0 else 1, seg4, inv_of, save=S)
+            else:
+                i = idx - 3
+                ms = 8 >> i  # hair_masks / back_masks pyramid level == stride into the full-resolution masks
+                x = blk.forward_nhwc(x, 1, seg4, inv_of, blend=(feats[i], hair, back, ms), save=S)
+            saved.append(S)
             if taps is not None:
-                taps["up_%d" % i] = x
+                taps[name] = x
         out = ops.conv_img(x, self.conv_img.weight.detach(), self.conv_img.bias.detach())  # generator.py:227-228
         self.last_taps = taps
+        if save is not None:
+            save.seg4, save.inv_of, save.saved, save.Sfc, save.Sbg, save.x_last, save.out = seg4, inv_of, saved, Sfc, Sbg, x, out
         return out

@@ -275,23 +275,28 @@ def conv_to1(x, w_oihw, bias, pad):
 
 # ------------------------------------------------------------------------------------------ norms
 def bn_sums(x):
-    """Per-channel (sum, sum of squares) of an NHWC tensor as a [2*C] float64 tensor."""
+    """Per-channel (sum, sum of squares) of an NHWC tensor as a [2*C + 1] float64 tensor; the spare last element carries
+    the sample count through the cross-rank exchange (sync_batchnorm.allreduce_sums)."""
     _chk(x, "x")
     Cc = x.shape[-1]
-    sums = torch.zeros(2 * Cc, device=x.device, dtype=torch.float64)
+    sums = torch.zeros(2 * Cc + 1, device=x.device, dtype=torch.float64)
     check(_lib.load().mg_bn_stats(_p(x), x.numel() // Cc, Cc, _p(sums), _stream()), "mg_bn_stats")
     return sums
 
 
-def bn_finalize(sums, count, count_unbiased, eps=1e-5, momentum=0.1, clamp_mode=0, running_mean=None, running_var=None,
+def bn_finalize(sums, count, unbiased_mult=1, eps=1e-5, momentum=0.1, clamp_mode=0, running_mean=None, running_var=None,
                 want_stats=False):
+    """count: number of samples behind `sums`, or 0.0 = read the all-reduced count from sums[2*C] on the device;
+    unbiased_mult: 4^s when the normalised tensor is the 2^s-upsampled view (running_var's unbiased factor)."""
     Cc = sums.numel() // 2
     nscale = torch.empty(Cc, device=sums.device, dtype=torch.float32)
     nshift = torch.empty(Cc, device=sums.device, dtype=torch.float32)
     mean = torch.empty(Cc, device=sums.device, dtype=torch.float32) if want_stats else None
     var = torch.empty(Cc, device=sums.device, dtype=torch.float32) if want_stats else None
     _chk(running_mean, "running_mean"); _chk(running_var, "running_var")
-    check(_lib.load().mg_bn_finalize(_p(sums), Cc, float(count), float(count_unbiased), eps, momentum, clamp_mode,
+    if count <= 0 and sums.numel() != 2 * Cc + 1:
+        raise ValueError("bn_finalize: a device-side count needs the [2*C + 1] sums layout")
+    check(_lib.load().mg_bn_finalize(_p(sums), Cc, float(count), float(unbiased_mult), eps, momentum, clamp_mode,
                                      _p(nscale), _p(nshift), _p(running_mean), _p(running_var), _p(mean), _p(var),
                                      _stream()), "mg_bn_finalize")
     if want_stats:
@@ -504,7 +509,7 @@ def spade_bwd(dh, h, g1, x, x_shift, nscale, nshift, act):
     N, H, W, Cc = dh.shape
     dgb = torch.empty((N, H, W, 2 * Cc), device=dh.device, dtype=torch.float32)
     dxhat = torch.empty_like(dh)
-    sums = torch.zeros(2 * Cc, device=dh.device, dtype=torch.float64)
+    sums = torch.zeros(2 * Cc + 1, device=dh.device, dtype=torch.float64)   # + the sample-count slot (see bn_sums)
     check(_lib.load().mg_spade_bwd(_p(dh), _p(h), _p(g1), _p(x), x_shift, N, H, W, Cc, _p(nscale), _p(nshift), act, spade_bn(Cc),
                                    _p(dgb), _p(dxhat), _p(sums), _stream()), "mg_spade_bwd")
     return dgb, dxhat, sums
@@ -544,8 +549,9 @@ def act_bwd(dy, y, act, pm1=None, pm2=None, round_tf32=False):
     return dz
 
 
-def instance_norm_act_fwd(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None):
-    """Training variant of instance_norm_act: also returns the (rstd, shift) table needed by in_bwd."""
+def instance_norm_act_fwd(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None, out16=None):
+    """Training variant of instance_norm_act: also returns the (rstd, shift) table needed by in_bwd.
+    -> (y, ss), or (y, ss, hi, lo|None) with out16=(fmt, want_lo) (16-bit operand copies for the next tensor-core conv)."""
     _chk(x, "x"); _chk(pmul, "pmul")
     N, H, W, Cc = x.shape
     sums = torch.zeros((N, 2, Cc), device=x.device, dtype=torch.float64)
@@ -553,8 +559,11 @@ def instance_norm_act_fwd(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None
     check(lib.mg_in_stats(_p(x), N, H * W, Cc, _p(sums), _stream()), "mg_in_stats")
     ss = torch.empty((N, 2, Cc), device=x.device, dtype=torch.float32)
     y = torch.empty_like(x)
-    check(lib.mg_in_apply(_p(x), _p(sums), _p(ss), _p(y), N, H * W, Cc, eps, act, int(round_out), _p(pmul), None, None, 0, _stream()),
-          "mg_in_apply")
+    hi, lo = _alloc16(tuple(x.shape), x.device, out16)
+    check(lib.mg_in_apply(_p(x), _p(sums), _p(ss), _p(y), N, H * W, Cc, eps, act, int(round_out), _p(pmul), _p(hi), _p(lo),
+                          (out16[0] if out16 else 0), _stream()), "mg_in_apply")
+    if out16 is not None:
+        return y, ss, hi, lo
     return y, ss
 
 

@@ -35,7 +35,7 @@ def test_ctypes_signatures_cover_the_header():
     from michigan_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_functions()
     lib = _lib.load()
-    assert lib.mg_version() == 1
+    assert lib.mg_version() == 2
     assert lib.mg_launch_count() >= 0
 
 

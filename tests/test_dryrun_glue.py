@@ -1,0 +1,85 @@
+"""Host-code smoke tests on the CPU-only build box: the whole Python glue of the CUDA path (forward in both modes, the
+hand-written backward, the trainer iteration) runs against a no-op library (tests/dryrun.py).  Values are meaningless;
+what is checked is that the code executes, calls only exported entry points, and produces tensors / gradients of the
+right shapes.  Numerics are the `-m gpu` tests' job."""
+import random
+
+import pytest
+import torch
+
+from dryrun import dry_run
+
+
+def _nets(size=64, ngf=64):
+    from michigan_b200 import networks
+    from michigan_b200.options import make_opt
+    opt = make_opt(is_train=True, ngf=ngf, ndf=64, crop_size=size, gpu_ids=[])
+    G = networks.SPADEBGenerator(opt).train()
+    D = networks.MultiscaleDiscriminator(opt).train()
+    return opt, G, D
+
+
+def _inputs(n, size):
+    from helpers import preprocessed
+    _, pre = preprocessed(dict(batch=n, size=size, data_seed=1))
+    return pre
+
+
+@pytest.mark.parametrize("mode", ["mixed16", "tf32"])
+def test_generator_and_discriminator_forward_backward_glue(mode):
+    from michigan_b200 import precision
+    old = precision.mode()
+    precision.set_mode(mode)
+    try:
+        opt, G, D = _nets()
+        pre = _inputs(2, 64)
+        random.seed(0)
+        with dry_run() as dr:
+            with torch.no_grad():
+                out = G(pre["input_ref"], orient_mask=pre["orient_mask"], image_ref=pre["image_ref"], input_tag=pre["input_tag"],
+                        noise=pre["noise"], image_tag=pre["image_tag"])
+            assert tuple(out.shape) == (2, 3, 64, 64)
+            n_nograd = len(dr.lib.calls)
+            fake = G(pre["input_ref"], orient_mask=pre["orient_mask"], image_ref=pre["image_ref"], input_tag=pre["input_tag"],
+                     noise=pre["noise"], image_tag=pre["image_tag"])
+            assert fake.requires_grad and tuple(fake.shape) == (2, 3, 64, 64)
+            cond = torch.zeros(2, 4, 64, 64)
+            x = torch.cat([torch.cat([cond, fake], 1), torch.cat([cond, pre["image_tag"]], 1)], 0)
+            outs = D(x)
+            assert len(outs) == 2 and all(len(o) == 5 for o in outs)
+            loss = sum((t * t).mean() for o in outs for t in o) + fake.mean()
+            loss.backward()
+            assert len(dr.lib.calls) > 3 * n_nograd
+        for name, p in list(G.named_parameters()) + list(D.named_parameters()):
+            if name.startswith("backgroud_enc.layer4"):
+                assert p.grad is None      # present in the state dict, never executed (encoder.py:284)
+            else:
+                assert p.grad is not None and p.grad.shape == p.shape, name
+        # eval mode forward (running statistics, stored u/v) and the reference's NCHW block signature
+        with dry_run():
+            with torch.no_grad():
+                G.eval()
+                G(pre["input_ref"], orient_mask=pre["orient_mask"], image_ref=pre["image_ref"], input_tag=pre["input_tag"],
+                  noise=pre["noise"], image_tag=pre["image_tag"])
+                D.eval()
+                D(x.detach())
+    finally:
+        precision.set_mode(old)
+
+
+def test_discriminator_only_backward_glue():
+    """D step: gradients for D's parameters only, input without grad; G step through a frozen D: input gradient only."""
+    opt, G, D = _nets()
+    x = torch.rand(4, 7, 64, 64)
+    with dry_run():
+        outs = D(x)
+        sum(t.mean() for o in outs for t in o).backward()
+        assert all(p.grad is not None for p in D.parameters())
+        for p in D.parameters():
+            p.grad = None
+        D.requires_grad_(False)
+        xg = x.clone().requires_grad_()
+        outs = D(xg)
+        sum(t.mean() for o in outs for t in o).backward()
+        assert xg.grad is not None and xg.grad.shape == xg.shape
+        assert all(p.grad is None for p in D.parameters())
