@@ -1,19 +1,25 @@
 """bench.py — headline benchmark of the MichiGAN hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload gen_fwd|train_step]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload both|gen_fwd|train_step]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): generator-only forward of netG=spadeb (ngf 64), batch 8 per GPU,
-512x512 synthetic inputs, train-mode statistics (the `generate_fake` of a training iteration:
-SyncBN batch statistics incl. the cross-rank exchange, spectral-norm power iteration), no grad.
-One "step" = one such forward over one batch.  Prints ONE JSON line (rank 0).
+BASELINE.json's metric has two halves, both measured by the default run and printed in ONE JSON line (rank 0):
 
-  value     images/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks
-  e2e       images/s through the public API (`Pix2PixModel(data, mode='inference')`-style call) with
-            pinned HOST buffers: H2D of the data dict and D2H of the generated image inside the timed region
-  roofline  the dominant kernel (fused SPADE gamma/beta implicit GEMM of up_3) timed alone, live
-  cpu_baseline / --impl reference   the CPU oracle port of the reference path on the host cores
+  top level   configs[1]: generator-only forward of netG=spadeb (ngf 64), batch 8 per GPU, 512x512 synthetic inputs,
+              train-mode statistics (the `generate_fake` of a training iteration: SyncBN batch statistics incl. the
+              cross-rank exchange, spectral-norm power iteration), no grad.  One "step" = one forward over one batch.
+  train_step  configs[2]: the full G+D train iteration (hinge GAN + GAN-feature losses, Adam TTUR), batch 8 per GPU,
+              512x512 synthetic; same keys as the top level (value, ms_per_step, e2e, roofline, gpu_launches).
+
+  value       images/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks.  A timed BLOCK is
+              exactly --steps steps between barrier + synchronize pairs; blocks are repeated until the leg has run for
+              >= 2 s (at most 8 blocks) and the MEDIAN block is reported (all block times are listed in `blocks_ms`).
+  e2e         images/s through the public API with pinned HOST buffers: H2D of the data dict and D2H of the result
+              (image / loss scalars) inside the timed region
+  roofline    the dominant kernel timed alone, live; roofline_worst: the kernel furthest below its roofline
+  cpu_baseline / --impl reference   the reference's own CPU implementation on the host cores: the UNMODIFIED reference
+              code staged under baseline/_ref (kind "reference") when present, else the CPU oracle port (kind "port")
 """
 import argparse
 import json
@@ -31,6 +37,10 @@ sys.path.insert(0, ROOT)
 BATCH_PER_GPU = 8
 SIZE = 512
 G_FWD_GFLOP_PER_IMG = 1114.2  # SURVEY.md §8d / BASELINE.md §3 (2*MAC, convs only)
+TRAIN_GFLOP_PER_IMG = 4775.8  # SURVEY.md §8d: G step + D step, hinge GAN + GAN-feature losses
+MIN_LEG_SECONDS = 2.0
+MAX_BLOCKS = 8
+CPU_THREADS = 32              # fixed: PyTorch's CPU convs stop scaling (and regress) beyond ~32 threads on the B200 hosts
 
 
 def parse():
@@ -39,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="gen_fwd", choices=["gen_fwd", "train_step"])
+    ap.add_argument("--workload", default="both", choices=["both", "gen_fwd", "train_step"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -87,50 +97,102 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def best_cpu_threads():
-    """The CPU arm gets every host thread it can USE: a 3x3 conv of the generator's shape is timed at several intra-op
-    thread counts (all cores down to 16) and the fastest is kept - on the 128-thread B200 hosts oversubscribing makes
-    PyTorch's CPU conv 3x slower than 16..32 threads (profiles/r01_cpu_threads.log)."""
-    import torch.nn.functional as F
+# ================================================================================================ CPU arm
+def cpu_threads():
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cands = sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16)})
-    x = torch.randn(1, 128, 256, 256)
-    w = torch.randn(128, 128, 3, 3)
-    best, best_t = cands[-1], float("inf")
-    for t in cands:
-        torch.set_num_threads(t)
-        F.conv2d(x, w, padding=1)
-        t0 = time.perf_counter()
-        for _ in range(2):
-            F.conv2d(x, w, padding=1)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = t, dt
-    return best
+    return max(1, min(ncpu, CPU_THREADS))
 
 
-def cpu_generator_forward_ips(steps, warmup, sample_images=1):
-    """The reference's generator forward restated on the CPU (oracle/michigan_oracle.py), all host threads."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import michigan_oracle as orc
-    from helpers import preprocessed, reference_layout_state
-    cores = best_cpu_threads()
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+REF_FLAGS = ("--use_encoder --wide_edge 2 --noise_background --random_expand_mask --no_confidence_loss --no_style_loss "
+             "--no_rgb_loss --no_content_loss --no_background_loss --no_vgg_loss --no_orient_loss --no_lab_loss --gpu_ids -1 "
+             "--no_html --batchSize 1 --checkpoints_dir /tmp/mg_bench_ref_ckpt").split()
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "models", "networks"))
+
+
+def _reference_trainer():
+    """The UNMODIFIED reference (baseline/_ref) on the CPU: its own option parser, class factory, Pix2PixTrainer."""
+    from michigan_b200 import compat
+    compat.stub_optional_imports()
+    compat.patch_adam_betas()
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import contextlib
+    import io
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    import models.networks as networks
+    compat.patch_style_content_loss(networks)
+    argv = sys.argv
+    sys.argv = ["bench"] + REF_FLAGS
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            from options.train_options import TrainOptions
+            opt = TrainOptions().parse()
+            from trainers.pix2pix_trainer import Pix2PixTrainer
+            trainer = Pix2PixTrainer(opt)
+    finally:
+        sys.argv = argv
+    return trainer
+
+
+def cpu_reference_ips(steps, warmup, train=False):
+    """images/s of the reference's CPU path, batch 1, 512x512, same net / synthetic inputs / deterministic weights.
+    -> (gen_fwd images/s, ms per forward, train images/s or None, cores, kind)."""
+    from michigan_b200.synth import fill_state_dict, synthetic_batch
+    cores = cpu_threads()
     torch.set_num_threads(cores)
-    cfg = dict(ngf=64, ndf=64, size=SIZE, batch=sample_images, data_seed=1234)
-    sd = reference_layout_state("G", cfg, 0)
-    _, pre = preprocessed(cfg)
-    opt = orc.default_opt(isTrain=True)
+    data = synthetic_batch(1, SIZE, 1234)
+    import random
+    if reference_available():
+        kind = "reference"
+        trainer = _reference_trainer()
+        m = trainer.pix2pix_model_on_one_gpu
+        fill_state_dict(m.netG.state_dict(), 0)
+        fill_state_dict(m.netD.state_dict(), 1)
+        m.train()
+
+        def fwd():
+            with torch.no_grad():
+                ins = m.preprocess_input(dict(data))
+                m.generate_fake(ins[0], ins[2], orient_mask=ins[4], input_tag=ins[1], image_tag=ins[3], noise=ins[7])
+
+        def train_it():
+            trainer.run_generator_one_step(dict(data))
+            trainer.run_discriminator_one_step(dict(data))
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import michigan_oracle as orc
+        from helpers import preprocessed, reference_layout_state
+        cfg = dict(ngf=64, ndf=64, size=SIZE, batch=1, data_seed=1234)
+        sd = reference_layout_state("G", cfg, 0)
+        _, pre = preprocessed(cfg)
+        oopt = orc.default_opt(isTrain=True)
+
+        def fwd():
+            with torch.no_grad():
+                orc.generate_fake(sd, oopt, pre, True, rng_k=25)
+        train_it = None
+    random.seed(0)
     times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            orc.generate_fake(sd, opt, pre, True, rng_k=25)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    total = sum(times)
-    return sample_images * len(times) / total, total / len(times) * 1e3, cores
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fwd()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    ips = len(times) / sum(times)
+    train_ips = None
+    if train and train_it is not None:
+        train_it()                              # warm-up (allocations, lazy init)
+        t0 = time.perf_counter()
+        train_it()
+        train_ips = 1.0 / (time.perf_counter() - t0)
+    return ips, sum(times) / len(times) * 1e3, train_ips, cores, kind
 
 
 def run_reference_arm(a):
@@ -138,29 +200,52 @@ def run_reference_arm(a):
     if rank != 0:
         return
     steps, warm = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
-    ips, ms, cores = cpu_generator_forward_ips(steps, warm, 1)
+    want_train = a.workload in ("both", "train_step")
+    ips, ms, train_ips, cores, kind = cpu_reference_ips(steps, warm, train=want_train)
+    what = "the unmodified reference (baseline/_ref) imported on the CPU" if kind == "reference" else "the CPU oracle port"
     line = {
         "impl": "reference", "metric": "512x512 images/sec (generator forward)", "value": ips, "unit": "images/s",
         "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "generator-only forward (netG=spadeb ngf64, train-mode statistics, no grad), 512x512 synthetic",
-                   "per_step_images": 1, "note": "CPU arm: bounded sample of 1 image per step on the host cores"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                   "per_step_images": 1, "note": "CPU arm (%s): bounded sample of 1 image per step on the host cores" % what},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": "%d timed forwards of 1 image (batch 1) after %d warm-up" % (steps, warm)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if train_ips is not None:
+        line["train_step"] = {"metric": "512x512 images/sec (train step)", "value": train_ips, "unit": "images/s",
+                              "ms_per_step": 1e3 / train_ips, "sample": "1 timed G+D iteration of 1 image after 1 warm-up",
+                              "e2e": {"value": train_ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------ native arm
-# DRAM traffic of one launch of the dominant kernel from the `ncu --set full` capture committed as
-# profiles/r01_ncu_spade_gemm_f16_final.txt (dram__bytes_read.sum 817.4 MB + dram__bytes_write.sum 1028.9 MB at N=8);
-# algorithmic bytes = actv fp16 268 MB + x fp32 268 MB + weights 0.6 MB read, bf16 hi+lo 537 MB written.
+# ================================================================================================ single-kernel rooflines
+# DRAM traffic of one launch of the dominant kernel from the `ncu --set full` capture committed under profiles/
+# (dram__bytes_read.sum + dram__bytes_write.sum at N=8); algorithmic bytes = actv fp16 268 MB + x fp32 268 MB + weights
+# 0.6 MB read, bf16 hi+lo 537 MB written.
 NCU_TRAFFIC_BYTES_N8 = 817.437696e6 + 1028.886e6
+NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_spade_gemm_f16_final.txt"
+
+
+def _time_kernel(f, reps=5):
+    flush = torch.empty(192 * 1024 * 1024 // 4, device="cuda")
+    for _ in range(3):
+        f()
+    times = []
+    for _ in range(reps):
+        flush.zero_()  # evict L2 (126 MB) between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        f()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return sorted(times)[len(times) // 2]
 
 
 def dominant_kernel_roofline(batch):
-    """Time the fused SPADE gamma/beta implicit GEMM of up_3.norm_0 alone, in the operand format the forward uses
+    """The fused SPADE gamma/beta implicit GEMM of up_3.norm_0 alone, in the operand format the forward uses
     (precision mode mixed16: fp16 operands, fp32 accumulate, bf16 hi/lo output; mode tf32: TF32 operands):
     A = actv [N,512,512,128], N_gemm = 2*128, K = 9*128, SPADE epilogue reading x [N,256,256,128] (upsample folded)
     and writing h [N,512,512,128].  FLOPs per launch = 2 * N*512*512 * 1152 * 256 (SURVEY.md Appendix A rows
@@ -171,7 +256,6 @@ def dominant_kernel_roofline(batch):
     wg = torch.randn(128, 128, 3, 3, device=dev) / 34
     xs = torch.randn(batch, SIZE // 2, SIZE // 2, 128, device=dev)
     v = torch.ones(128, device=dev)
-    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
     if precision.mode() == "tf32":
         wp = ops.pack_weight_gb(wg, wg)
         kind = "kind::tf32"
@@ -182,42 +266,90 @@ def dominant_kernel_roofline(batch):
         kind = "kind::f16"
         f = lambda: ops.conv_igemm(a16, wp, 128, 3, 3, 1, 1, act=2, a_fmt=ops.F16, spade=(xs, 1, v, v, v, v),
                                    out16=(ops.BF16, True), want_f32=False)
-    for _ in range(3):
-        f()
-    times = []
-    for _ in range(5):
-        flush.zero_()  # evict L2 (126 MB) between timed launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        f()
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sorted(times)[len(times) // 2]
+    ms = _time_kernel(f)
     flops = 2.0 * batch * SIZE * SIZE * 1152 * 256
     return flops / (ms * 1e-3) / 1e12, ms, flops, kind
 
 
-def run_native(a):
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from michigan_b200 import _lib
-    from michigan_b200.options import make_opt
-    from michigan_b200.pix2pix_model import Pix2PixModel
-    from michigan_b200.synth import fill_state_dict, synthetic_batch
+def worst_kernel_roofline(batch):
+    """The kernel furthest below its roofline among those that matter: the split-precision generic
+    conv at its thinnest shape, up_3.conv_0 = 3x3, 128 -> 64 at 512x512 (bf16 hi+lo operands, 3 products = 2 MMAs per K
+    step), 2 * N*512*512 * 1152 * 64 algorithmic FLOPs per launch (19.3 GF per image)."""
+    from michigan_b200 import ops, precision
+    dev = "cuda"
+    x = torch.randn(batch, SIZE, SIZE, 128, device=dev)
+    w = torch.randn(64, 128, 3, 3, device=dev) / 34
+    b = torch.zeros(64, device=dev)
+    if precision.mode() == "tf32":
+        wp = ops.pack_weight(w, None, True)
+        f = lambda: ops.conv_igemm(x, wp, 64, 3, 3, 1, 1, bias=b)
+        kind = "kind::tf32, one pass"
+    else:
+        hi = x.bfloat16()
+        lo = (x - hi.float()).bfloat16()
+        wp = ops.pack_weight16(w, None, ops.BF16, split=True)
+        f = lambda: ops.conv_igemm(hi, wp, 64, 3, 3, 1, 1, bias=b, a_fmt=ops.BF16, x_lo=lo)
+        kind = "kind::f16 bf16 hi+lo split"
+    ms = _time_kernel(f)
+    flops = 2.0 * batch * SIZE * SIZE * 1152 * 64
+    return flops / (ms * 1e-3) / 1e12, ms, flops, kind
 
-    if a.workload == "train_step":
-        return run_train_step(a, rank, world, local)
-    torch.manual_seed(0)
-    opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world)
-    model = Pix2PixModel(opt)
-    fill_state_dict(model.netG.state_dict(), 0)  # random-init weights of the reference architecture (109.5 M params)
-    model.netG.train()
+
+def wgrad_kernel_roofline(batch):
+    """Dominant kernel of the train step (27 % of it): the weight-gradient GEMM, at the shape of the SPADE
+    gamma|beta wgrad of up_3 (dY = dgamma|dbeta [N,512,512,256], X = actv [N,512,512,128], 3x3): 2 * N*512*512 * 1152 * 256
+    FLOPs per launch, TF32 operands."""
+    from michigan_b200 import ops
+    dev = "cuda"
+    dy = torch.randn(batch, SIZE, SIZE, 256, device=dev)
+    x = torch.randn(batch, SIZE, SIZE, 128, device=dev)
+    f = lambda: ops.conv_wgrad(dy, x, 3, 3, 1, 1)
+    ms = _time_kernel(f, reps=3)
+    flops = 2.0 * batch * SIZE * SIZE * 1152 * 256
+    return flops / (ms * 1e-3) / 1e12, ms, flops
+
+
+# ================================================================================================ native arm
+def timed_blocks(step, steps, world):
+    """Repeat [barrier+sync | e0 | `steps` x step | e1 | barrier+sync] until >= MIN_LEG_SECONDS have been timed; every block
+    time is the max over ranks (so all ranks agree on when to stop).  Returns the list of block times in ms."""
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    blocks = []
+    while True:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        blocks.append(float(ms.item()))
+        if sum(blocks) >= MIN_LEG_SECONDS * 1e3 or len(blocks) >= MAX_BLOCKS:
+            return blocks
+
+
+def median(v):
+    s = sorted(v)
+    return s[len(s) // 2] if len(s) % 2 else 0.5 * (s[len(s) // 2 - 1] + s[len(s) // 2])
+
+
+INPUT_KEYS = ("label_ref", "label_tag", "image_ref", "image_tag", "orient", "noise")
+
+
+def gen_fwd_leg(a, rank, world, local, model):
+    """-> dict of the top-level keys of the JSON line."""
+    import torch.distributed as dist
+    from michigan_b200 import _lib, precision
+    from michigan_b200.synth import synthetic_batch
     batch = a.batch
     data = synthetic_batch(batch, SIZE, 1234 + rank)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
@@ -228,7 +360,6 @@ def run_native(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
     with torch.no_grad():
         pre = model.preprocess_input(host)
         torch.cuda.synchronize()
@@ -243,18 +374,10 @@ def run_native(a):
         if rank == 0:
             sampler.start()
         l0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.steps):
-            out = step()
-        e1.record()
-        barrier()
-        launches = _lib.launch_count() - l0
+        blocks = timed_blocks(step, a.steps, world)
+        launches = (_lib.launch_count() - l0) // len(blocks)
         clocks = sampler.stop() if rank == 0 else None
-        ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-        ms_total = ms_total.item()
+        ms_block = median(blocks)
 
         # ---- end to end through the public API with host buffers.  Every step copies its inputs from pinned host memory
         # and reads its result back into pinned host memory; like a prefetching data loader the copies run on a second
@@ -263,8 +386,6 @@ def run_native(a):
         main_stream = torch.cuda.current_stream()
         host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
         tensor_keys = [k for k, v in host.items() if torch.is_tensor(v)]
-
-        # two device-side input sets allocated once (no allocator traffic on the copy stream)
         dev_sets = [{k: torch.empty_like(host[k], device="cuda") for k in tensor_keys} for _ in range(2)]
 
         def prefetch(i):
@@ -295,8 +416,8 @@ def run_native(a):
             main_stream.synchronize()
 
         e2e_run(max(2, a.warmup // 2 + 1))
+        e2e_steps = a.steps * max(1, min(MAX_BLOCKS, len(blocks)))
         barrier()
-        e2e_steps = a.steps
         t0 = time.perf_counter()
         e2e_run(e2e_steps)
         barrier()
@@ -305,46 +426,173 @@ def run_native(a):
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         t_e2e = t_e2e.item()
 
-    h2d = sum(v.numel() * v.element_size() for k, v in host.items()
-              if torch.is_tensor(v) and k in ("label_ref", "label_tag", "image_ref", "image_tag", "orient", "noise"))
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v) and k in INPUT_KEYS)
     d2h = host_out.numel() * 4
+    ms_step = ms_block / a.steps
+    return {
+        "metric": "512x512 images/sec (generator forward)", "value": world * batch * a.steps / (ms_block * 1e-3), "unit": "images/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": DTYPE_NOTE[precision.mode()], "data": "synthetic",
+        "config": {"workload": "generator-only forward (netG=spadeb ngf64, 109.5M params, train-mode statistics, no grad), "
+                               "batch %d/GPU, 512x512 synthetic mask/orient/ref inputs" % batch,
+                   "global_batch": batch * world, "parallelism": "dp%d" % world,
+                   "l2": "no explicit flush: each step streams multi-GB NHWC activations (>> 126 MB L2)",
+                   "algorithmic_gflop_per_image": G_FWD_GFLOP_PER_IMG,
+                   "timing": "median of %d blocks of %d steps (>= %.0f s timed)" % (len(blocks), a.steps, MIN_LEG_SECONDS)},
+        "blocks_ms": blocks,
+        "achieved_tflops_step": G_FWD_GFLOP_PER_IMG * batch / ms_step,
+        "e2e": {"value": world * batch * e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps,
+                "how": "Pix2PixModel(data, mode='inference') per step; pinned host inputs -> device and image -> pinned host every "
+                       "step, copies double-buffered on a second stream (prefetching-loader style), wall clock"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
 
+
+def train_step_leg(a, rank, world, local, model):
+    """BASELINE.json configs[2]: one generator update + one discriminator update per step (train.py:94-101)."""
+    import torch.distributed as dist
+    from michigan_b200 import _lib
+    from michigan_b200.networks.sync_batchnorm import DataParallelWithCallback, exchange_backend
+    from michigan_b200.pix2pix_model import train_iteration
+    from michigan_b200.synth import synthetic_batch
+    batch = a.batch
+    wrap = DataParallelWithCallback(model, device_ids=[local])
+    optG, optD = model.create_optimizers(model.opt)
+    data = synthetic_batch(batch, SIZE, 1234 + rank)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+    last = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        g, d, _ = train_iteration(wrap, optG, optD, dict(dev))
+        last["losses"] = {**g, **d}
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    t_host0 = time.perf_counter()
+    blocks = timed_blocks(step, a.steps, world)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / (a.steps * len(blocks))
+    launches = (_lib.launch_count() - l0) // len(blocks)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_block = median(blocks)
+
+    # ---- end to end: every step starts from pinned HOST tensors (H2D inside) and ends with the loss scalars on the host
+    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        g, d, _ = train_iteration(wrap, optG, optD, dict(host))
+        vals = torch.stack([v.mean() for v in {**g, **d}.values()])
+        loss_host[: vals.numel()].copy_(vals, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return vals.numel()
+
+    e2e_step()
+    e2e_steps = a.steps
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        nl = e2e_step()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = t_e2e.item()
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v) and k in INPUT_KEYS) * 2   # G step + D step
+    ms_step = ms_block / a.steps
+    out = {
+        "metric": "512x512 images/sec (train step)", "value": world * batch * a.steps / (ms_block * 1e-3), "unit": "images/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "dtype": "forward: fp16/bf16 tensor-core operands as the generator-forward leg; gradient GEMMs: TF32 operands; fp32 accumulate, "
+                 "storage, statistics and Adam",
+        "config": {"workload": "full G+D train iteration (hinge GAN + GAN-feature losses, Adam TTUR), netG=spadeb ngf64, "
+                               "netD=multiscale ndf64, batch %d/GPU, 512x512 synthetic" % batch,
+                   "global_batch": batch * world, "parallelism": "dp%d" % world,
+                   "l2": "no explicit flush: multi-GB activations per step", "algorithmic_gflop_per_image": TRAIN_GFLOP_PER_IMG,
+                   "timing": "median of %d blocks of %d steps" % (len(blocks), a.steps),
+                   "syncbn_exchange": exchange_backend(), "grad_allreduce": "in-backward staged NCCL all-reduce (AVG) of a flat fp32 buffer"},
+        "blocks_ms": blocks,
+        "achieved_tflops_step": TRAIN_GFLOP_PER_IMG * batch / ms_step,
+        "e2e": {"value": world * batch * e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * nl,
+                "steps": e2e_steps,
+                "how": "train_iteration(DataParallelWithCallback(Pix2PixModel), ...) per step from pinned host tensors; the loss "
+                       "scalars are copied to pinned host memory and the stream is synchronised every step; wall clock"},
+        "gpu_launches": launches, "clocks": clocks, "host_enqueue_ms_per_step": host_ms,
+        "losses": {k: float(v.mean()) for k, v in last["losses"].items()},
+    }
+    return out
+
+
+def run_native(a):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from michigan_b200.options import make_opt
+    from michigan_b200.pix2pix_model import Pix2PixModel
+    from michigan_b200.synth import fill_state_dict
+
+    torch.manual_seed(0)
+    opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world, niter=50, niter_decay=0)
+    model = Pix2PixModel(opt)
+    fill_state_dict(model.netG.state_dict(), 0)  # random-init weights of the reference architecture (109.5 M params)
+    fill_state_dict(model.netD.state_dict(), 1)
+    model.train()
+
+    line = None
+    if a.workload in ("both", "gen_fwd"):
+        line = gen_fwd_leg(a, rank, world, local, model)
+    train = None
+    if a.workload in ("both", "train_step"):
+        train = train_step_leg(a, rank, world, local, model)
     if rank == 0:
         pk, pk_kind = peaks()
-        tf, kms, kflops, kkind = dominant_kernel_roofline(batch)
-        from michigan_b200 import precision
         peak_tf = float(pk["bf16_tflops"])
-        ms_step = ms_total / a.steps
-        value = world * batch * a.steps / (ms_total * 1e-3)
-        line = {
-            "metric": "512x512 images/sec (generator forward)", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": DTYPE_NOTE[precision.mode()], "data": "synthetic",
-            "config": {"workload": "generator-only forward (netG=spadeb ngf64, 109.5M params, train-mode statistics, no grad), "
-                                   "batch %d/GPU, 512x512 synthetic mask/orient/ref inputs" % batch,
-                       "global_batch": batch * world, "parallelism": "dp%d" % world,
-                       "l2": "no explicit flush: each step streams multi-GB NHWC activations (>> 126 MB L2)",
-                       "algorithmic_gflop_per_image": G_FWD_GFLOP_PER_IMG},
-            "achieved_tflops_step": G_FWD_GFLOP_PER_IMG * batch / ms_step,
-            "e2e": {"value": world * batch * e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
-                    "how": "Pix2PixModel(data, mode='inference') per step; pinned host inputs -> device and image -> pinned host every "
-                           "step, copies double-buffered on a second stream (prefetching-loader style), wall clock"},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"kernel": "igemm_tf32_kernel<1,16> (fused SPADE gamma|beta implicit GEMM + modulate + LeakyReLU, up_3.norm_0 shape, "
-                                   "tcgen05 %s)" % kkind,
-                         "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": NCU_TRAFFIC_BYTES_N8 * batch / 8 if kkind == "kind::f16" else None,
-                         "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01_ncu_spade_gemm_f16_final.txt)",
-                         "peak_kind": "%s bf16 dense burst (MEASURED_PEAKS.json)%s" % (
-                             pk_kind, "; kind::tf32 issues at half the bf16 rate" if kkind == "kind::tf32" else ""),
-                         "ms_per_launch": kms, "flops_per_launch": kflops},
-        }
+        if line is not None:
+            tf, kms, kflops, kkind = dominant_kernel_roofline(a.batch)
+            line["roofline"] = {
+                "kernel": "igemm_tf32_kernel<1,16> (fused SPADE gamma|beta implicit GEMM + modulate + LeakyReLU, up_3.norm_0 shape, tcgen05 %s)" % kkind,
+                "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                "traffic": NCU_TRAFFIC_BYTES_N8 * a.batch / 8 if kkind == "kind::f16" else None,
+                "traffic_unit": "bytes per launch (dram read + write, ncu --set full, %s)" % NCU_TRAFFIC_SOURCE,
+                "peak_kind": "%s bf16 dense burst (MEASURED_PEAKS.json)%s" % (
+                    pk_kind, "; kind::tf32 issues at half the bf16 rate" if kkind == "kind::tf32" else ""),
+                "ms_per_launch": kms, "flops_per_launch": kflops}
+            wtf, wms, wflops, wkind = worst_kernel_roofline(a.batch)
+            line["roofline_worst"] = {
+                "kernel": "igemm_tf32_kernel<0,16> (generic implicit-GEMM conv, up_3.conv_0 shape 3x3 128->64 at 512x512, %s)" % wkind,
+                "bound": "tensor", "achieved": wtf, "peak": peak_tf, "unit": "TFLOP/s", "frac": wtf / peak_tf, "traffic": None,
+                "note": "algorithmic FLOPs (one product per MAC); the split-precision form issues 3 products per MAC",
+                "ms_per_launch": wms, "flops_per_launch": wflops}
+        if train is not None:
+            gtf, gms, gflops = wgrad_kernel_roofline(a.batch)
+            train["roofline"] = {
+                "kernel": "wgrad_tf32_kernel (weight-gradient GEMM, SPADE gamma|beta wgrad of up_3: K = N*512*512 pixels, 256 x 1152 outputs, tcgen05 kind::tf32)",
+                "bound": "tensor", "achieved": gtf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gtf / peak_tf, "traffic": None,
+                "peak_kind": "%s bf16 dense burst; kind::tf32 issues at half the bf16 rate" % pk_kind,
+                "ms_per_launch": gms, "flops_per_launch": gflops}
+        if line is None:
+            line = train
+        elif train is not None:
+            train.pop("clocks_unused", None)
+            line["train_step"] = train
         if not a.no_cpu_baseline and world == 1:
-            ips, ms_cpu, cores = cpu_generator_forward_ips(3, 1, 1)
-            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": "3 timed forwards of 1 image (batch 1, same net/size) after 1 warm-up"}
+            ips, ms_cpu, train_ips, cores, kind = cpu_reference_ips(3, 1, train=False)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                                    "sample": "3 timed generator forwards of 1 image (batch 1, same net/size) after 1 warm-up"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -354,80 +602,6 @@ DTYPE_NOTE = {
     "mixed16": "fp16/bf16 tensor-core operands (bf16 hi+lo split where needed), fp32 accumulate and storage",
     "tf32": "tf32",
 }
-
-TRAIN_GFLOP_PER_IMG = 4775.8  # SURVEY.md §8d: G step + D step, hinge GAN + GAN-feature losses
-
-
-def run_train_step(a, rank, world, local):
-    """BASELINE.json configs[2]: full G+D train iteration (run_generator_one_step + run_discriminator_one_step),
-    batch 8 per GPU, 512x512 synthetic; secondary metric (`--workload train_step`)."""
-    import torch.distributed as dist
-    from michigan_b200 import _lib
-    from michigan_b200.options import make_opt
-    from michigan_b200.synth import fill_state_dict, synthetic_batch
-    from michigan_b200.trainer import Pix2PixTrainer
-    torch.manual_seed(0)
-    opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world, niter=50, niter_decay=0)
-    trainer = Pix2PixTrainer(opt)
-    m = trainer.pix2pix_model_on_one_gpu
-    fill_state_dict(m.netG.state_dict(), 0)
-    fill_state_dict(m.netD.state_dict(), 1)
-    m.train()
-    data = synthetic_batch(a.batch, SIZE, 1234 + rank)
-    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step():
-        trainer.run_generator_one_step(dict(host))
-        trainer.run_discriminator_one_step(dict(host))
-
-    for _ in range(a.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t_host0 = time.perf_counter()
-    for _ in range(a.steps):
-        step()
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / a.steps   # CPU time to issue one step (no sync inside)
-    e1.record()
-    barrier()
-    launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = ms_total.item()
-    if rank == 0:
-        ms_step = ms_total / a.steps
-        losses = {k: float(v.mean()) for k, v in trainer.get_latest_losses().items()}
-        h2d = sum(v.numel() * v.element_size() for k, v in host.items()
-                  if torch.is_tensor(v) and k in ("label_ref", "label_tag", "image_ref", "image_tag", "orient", "noise")) * 2
-        value = world * a.batch * a.steps / (ms_total * 1e-3)
-        line = {
-            "metric": "512x512 images/sec (train step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "full G+D train iteration (hinge GAN + GAN-feature losses, Adam TTUR), netG=spadeb ngf64, "
-                                   "netD=multiscale ndf64, batch %d/GPU, 512x512 synthetic" % a.batch,
-                       "global_batch": a.batch * world, "parallelism": "dp%d" % world,
-                       "l2": "no explicit flush: multi-GB activations per step", "algorithmic_gflop_per_image": TRAIN_GFLOP_PER_IMG},
-            "achieved_tflops_step": TRAIN_GFLOP_PER_IMG * a.batch / ms_step,
-            # the step already starts from host (pinned) tensors and returns host-visible loss scalars
-            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(losses)},
-            "gpu_launches": launches, "clocks": clocks, "losses": losses, "host_enqueue_ms_per_step": host_enqueue_ms,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

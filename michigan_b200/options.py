@@ -22,6 +22,9 @@ def make_opt(is_train=True, **overrides):
         # train options
         ndf=64, netD="multiscale", netD_subarch="n_layer", num_D=2, n_layers_D=4, lambda_feat=1.0, no_gan_loss=False,
         no_ganFeat_loss=False, gan_mode="hinge", no_TTUR=False, lr=0.0002, beta1=0.5, beta2=0.999, wide_edge=2.0,
+        # loss switches: the stand-alone model implements hinge GAN + GAN_Feat (SURVEY.md §8d flag set)
+        no_vgg_loss=True, no_style_loss=True, no_content_loss=True, no_background_loss=True, no_rgb_loss=True, no_lab_loss=True,
+        no_orient_loss=True, no_confidence_loss=True,
         isTrain=is_train,
     )
     for k, v in overrides.items():

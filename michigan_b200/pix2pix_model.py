@@ -29,6 +29,16 @@ class Pix2PixModel(torch.nn.Module):
         for flag in ("use_vae", "use_blender", "use_instance_feat", "unpairTrain"):
             if getattr(opt, flag, False):
                 raise NotImplementedError("michigan_b200: --%s is outside the hot path (SURVEY.md §8)" % flag)
+        if opt.isTrain:
+            # The reference's generator objective also contains VGG / style / content / background / rgb / lab / orientation
+            # terms, all ON by default (pix2pix_model.py:296-345).  This stand-alone model implements the SURVEY §8d loss set
+            # (hinge GAN + GAN feature matching): anything else must be switched off explicitly rather than silently dropped.
+            # (Through michigan_b200.install() the reference's own Pix2PixModel computes whatever losses it is asked for.)
+            missing = [f for f in ("no_vgg_loss", "no_style_loss", "no_content_loss", "no_background_loss", "no_rgb_loss",
+                                   "no_lab_loss", "no_orient_loss") if not getattr(opt, f, False)]
+            if missing:
+                raise NotImplementedError("michigan_b200.Pix2PixModel trains with the hinge GAN + GAN_Feat losses only; pass --%s "
+                                          "(or drive the reference's Pix2PixModel through michigan_b200.install())" % " --".join(missing))
         self.netIG = None
         if getattr(opt, "use_ig", False):
             self.netIG = networks.define_IG(opt)
@@ -56,11 +66,12 @@ class Pix2PixModel(torch.nn.Module):
                 load_weights(self.netD, torch.load(self._ckpt_path("D", epoch), map_location="cpu"))
 
     def save(self, epoch):
-        """<checkpoints_dir>/<name>/<epoch>_net_{G,D}.pth, CPU state dicts with the reference's keys."""
-        os.makedirs(os.path.dirname(self._ckpt_path("G", epoch)), exist_ok=True)
-        torch.save({k: v.cpu() for k, v in self.netG.state_dict().items()}, self._ckpt_path("G", epoch))
+        """<checkpoints_dir>/<name>/<epoch>_net_{G,D}.pth, CPU state dicts with the reference's keys (util.py:195-200):
+        rank 0 writes (snapshot copied on a side stream, serialised by a background thread), all ranks meet at a barrier."""
+        from . import checkpoint
+        checkpoint.save_state_dict(self.netG, self._ckpt_path("G", epoch))
         if self.netD is not None:
-            torch.save({k: v.cpu() for k, v in self.netD.state_dict().items()}, self._ckpt_path("D", epoch))
+            checkpoint.save_state_dict(self.netD, self._ckpt_path("D", epoch))
 
     def _load_inpainting_network(self, opt):
         """util.load_inpainting_network (util.py:245-257): <checkpoints_dir>/<name>/<ig_model_name> = {'generator': state_dict}."""
@@ -116,7 +127,7 @@ class Pix2PixModel(torch.nn.Module):
     # ------------------------------------------------------------------ helpers
     def preprocess_input(self, data):
         """pix2pix_model.py:209-254: host->device copies and the one-hot label maps."""
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = _device()
 
         def dv(t):
             return t.to(dev, non_blocking=True)
@@ -159,7 +170,10 @@ class Pix2PixModel(torch.nn.Module):
     def compute_generator_loss(self, input_ref, input_tag, image_ref, image_tag, orient_mask, noise):
         G_losses = {}
         fake_image = self.generate_fake(input_ref, image_ref, orient_mask, input_tag, image_tag, noise)
-        pred_fake, pred_real = self.discriminate(input_tag, fake_image, image_tag, orient_mask)
+        # The discriminator's parameters are constants of the generator's objective: the reference back-propagates into
+        # them anyway and discards the result (optimizer_D.zero_grad() precedes their only use, pix2pix_trainer.py:62-69).
+        with _frozen(self.netD):
+            pred_fake, pred_real = self.discriminate(input_tag, fake_image, image_tag, orient_mask)
         label_tag = input_tag[:, 1:2]
         if not self.opt.no_gan_loss:
             G_losses["GAN"] = self.criterionGAN(pred_fake, True, for_discriminator=False, label=label_tag)
@@ -179,6 +193,42 @@ class Pix2PixModel(torch.nn.Module):
 
     def use_gpu(self):
         return True
+
+
+def _device():
+    """This process's CUDA device (tests/dryrun.py substitutes the CPU for host-logic tests)."""
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _frozen:
+    """with _frozen(net): parameters temporarily do not require grad (their gradients are neither computed nor reduced)."""
+
+    def __init__(self, net):
+        self.flags = [(p, p.requires_grad) for p in net.parameters()]
+
+    def __enter__(self):
+        for p, _ in self.flags:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p, r in self.flags:
+            p.requires_grad_(r)
+        return False
+
+
+def train_iteration(model, optimizer_G, optimizer_D, data):
+    """One generator update followed by one discriminator update on `data` (what train.py's inner loop does per batch,
+    train.py:94-101, with D_steps_per_G = 1): returns (g_losses, d_losses, generated).  `model` may be wrapped in
+    DataParallelWithCallback; gradients are already rank-averaged when backward() returns."""
+    optimizer_G.zero_grad(set_to_none=True)
+    g_losses, generated = model(data, mode="generator")
+    torch.stack([v.mean() for v in g_losses.values()]).sum().backward()
+    optimizer_G.step()
+    optimizer_D.zero_grad(set_to_none=True)
+    d_losses = model(data, mode="discriminator")
+    torch.stack([v.mean() for v in d_losses.values()]).sum().backward()
+    optimizer_D.step()
+    return g_losses, d_losses, generated
 
 
 def load_weights(net, pretrained):

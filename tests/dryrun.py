@@ -51,8 +51,21 @@ def dry_run():
     real_empty, real_empty_like = torch.empty, torch.empty_like
     torch.empty = lambda *a, **k: torch.zeros(*a, **k)
     torch.empty_like = lambda *a, **k: torch.zeros_like(*a, **k)
+    # the stand-alone Pix2PixModel insists on a CUDA device: keep everything on the CPU for the dry run
+    from michigan_b200 import networks, pix2pix_model
+    saved_dev, saved_create = pix2pix_model._device, networks.create_network
+    pix2pix_model._device = lambda: torch.device("cpu")
+
+    def create_network(cls, opt):
+        net = cls(opt)
+        net.print_network()
+        net.init_weights(opt.init_type, opt.init_variance)
+        return net
+
+    networks.create_network = create_network
     try:
         yield SimpleNamespace(lib=fake)
     finally:
         _lib._lib, ops._chk, ops._stream = saved
         torch.empty, torch.empty_like = real_empty, real_empty_like
+        pix2pix_model._device, networks.create_network = saved_dev, saved_create

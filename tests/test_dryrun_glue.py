@@ -83,3 +83,30 @@ def test_discriminator_only_backward_glue():
         sum(t.mean() for o in outs for t in o).backward()
         assert xg.grad is not None and xg.grad.shape == xg.shape
         assert all(p.grad is None for p in D.parameters())
+
+
+def test_standalone_model_train_iteration_glue(tmp_path):
+    """michigan_b200.Pix2PixModel + train_iteration (what bench.py's train-step leg and the NCCL parity worker drive):
+    generator step with the discriminator frozen, discriminator step, checkpoint layout; loss flags must be explicit."""
+    import os
+    from michigan_b200 import checkpoint
+    from michigan_b200.options import make_opt
+    from michigan_b200.pix2pix_model import Pix2PixModel, train_iteration
+    from michigan_b200.synth import synthetic_batch
+    with dry_run():
+        opt = make_opt(is_train=True, ngf=64, ndf=64, crop_size=64, batchSize=2, checkpoints_dir=str(tmp_path), name="dry")
+        with pytest.raises(NotImplementedError):
+            Pix2PixModel(make_opt(is_train=True, ngf=64, ndf=64, crop_size=64, no_vgg_loss=False))
+        model = Pix2PixModel(opt).train()
+        optG, optD = model.create_optimizers(opt)
+        data = synthetic_batch(2, 64, 1)
+        random.seed(0)
+        g, d, img = train_iteration(model, optG, optD, dict(data))
+        assert set(g) == {"GAN", "GAN_Feat"} and set(d) == {"D_Fake", "D_real"} and tuple(img.shape) == (2, 3, 64, 64)
+        assert all(p.requires_grad for p in model.netD.parameters())       # un-frozen again after the generator step
+        model.save("latest")
+        checkpoint.wait_pending()
+        sd = torch.load(os.path.join(tmp_path, "dry", "latest_net_G.pth"))
+        assert list(sd.keys()) == list(model.netG.state_dict().keys())
+        out = model(dict(data), mode="inference")
+        assert tuple(out.shape) == (2, 3, 64, 64) and not out.requires_grad

@@ -68,6 +68,40 @@ def test_generator_train_mode_vs_golden_and_oracle():
     assert all(int(v) == 0 for k, v in got.items() if k.endswith("num_batches_tracked"))
 
 
+def test_generator_training_forward_image_vs_golden():
+    """The image returned by the TRAINING forward (grad enabled: the autograd Function that `mode='generator'` runs,
+    pix2pix_model.py:505-541) against the reference's train-mode output, at the same bound as the no-grad forward:
+    max-abs <= 1e-3, mean-abs <= 2e-4.  Both modes share one forward implementation and one operand policy."""
+    z, cfg = load_golden()
+    sd = reference_layout_state("G", cfg, cfg["seed_G"])
+    G, opt = _build_G(cfg, True, sd)
+    G.train()
+    _, pre = preprocessed(cfg)
+    p = _cuda(pre)
+    random.seed(cfg["py_seed"])
+    out = G(p["input_ref"], orient_mask=p["orient_mask"], image_ref=p["image_ref"], input_tag=p["input_tag"], noise=p["noise"],
+            image_tag=p["image_tag"])
+    assert out.requires_grad and out.grad_fn is not None
+    mx, mn = max_mean_abs(out, torch.from_numpy(z["g_train_out"]))
+    print("G TRAINING forward (autograd) vs reference fixture: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
+    # bit-identical to the no-grad forward from the same state (same kernels, same operands)
+    G2, _ = _build_G(cfg, True, sd)
+    G2.train()
+    random.seed(cfg["py_seed"])
+    out2 = _run_G(G2, pre)
+    d = (out.detach() - out2).abs().max().item()
+    print("   training forward vs no-grad forward: max diff %.2e" % d)
+    assert d <= 2e-6
+    got = G.state_dict()
+    for k in z.files:
+        if k.startswith("g_post/"):
+            name = k[len("g_post/"):]
+            r = torch.from_numpy(z[k])
+            tol = 2e-3 if name.endswith(("running_mean", "running_var")) else 1e-4
+            assert (got[name].cpu() - r).abs().max().item() <= tol * max(1.0, r.abs().max().item()), name
+
+
 def test_generator_eval_mode_vs_golden():
     z, cfg = load_golden()
     sd = reference_layout_state("G", cfg, cfg["seed_G"])
@@ -139,6 +173,61 @@ def test_generator_full_size_vs_oracle():
         ref = orc.generate_fake(sd, oopt, pre, True, rng_k=k)
     mx, mn = max_mean_abs(out, ref)
     print("G 512x512 ngf64 vs oracle: max-abs %.3e mean-abs %.3e (output std %.3f)" % (mx, mn, ref.std().item()))
+    assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
+
+
+def test_generator_batch8_train_mode_vs_oracle():
+    """BASELINE.json configs[1]/[2] shape exactly: batch 8, 512x512, ngf 64, TRAIN-mode batch statistics over the 8
+    samples, against the oracle on the host CPU (~25 s)."""
+    cfg = dict(ngf=64, ndf=64, size=512, batch=8, data_seed=7)
+    sd = reference_layout_state("G", cfg, 23)
+    G, opt = _build_G(cfg, True, sd, batchSize=8)
+    G.train()
+    _, pre = preprocessed(cfg)
+    g = torch.Generator().manual_seed(2)
+    pre["image_ref"] = torch.rand(8, 3, 512, 512, generator=g) * 2 - 1     # a different image per sample
+    pre["image_tag"] = pre["image_ref"].clone()
+    random.seed(11)
+    th = int(512 * 0.05); th = th if th % 2 == 1 else th + 1
+    k = random.choice([max(th - 4, 1), max(th - 2, 1), th, th + 2, th + 4])
+    random.seed(11)
+    out = _run_G(G, pre)
+    with torch.no_grad():
+        ref = orc.generate_fake(sd, orc.default_opt(isTrain=True), pre, True, rng_k=k)
+    mx, mn = max_mean_abs(out, ref)
+    print("G batch 8 x 512x512 train-mode vs oracle: max-abs %.3e mean-abs %.3e (output std %.3f)" % (mx, mn, ref.std().item()))
+    assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
+
+
+def test_generator_add_feat_zeros_576_eval_vs_oracle():
+    """BASELINE.json configs[0]'s geometry: inference with --add_feat_zeros => every input zero-padded by add_th/2 = 32
+    on each side (pix2pix_model.py:240-254), the generator runs at 576x576 with a 9x9 latent (generator.py:79-96), and the
+    eval-mode background mask dilates only inside the original window (encoder.py:301-314)."""
+    from michigan_b200.options import make_opt
+    from michigan_b200.pix2pix_model import Pix2PixModel
+    from michigan_b200.synth import synthetic_batch
+    cfg = dict(ngf=64, ndf=64, size=512, batch=1, data_seed=13)
+    sd = reference_layout_state("G", dict(cfg, size=512), 24)
+    # calibrate the running statistics (fill_state_dict leaves mean 0 / var 1): one train-mode oracle pass at 256x256 with
+    # momentum 1 writes the batch statistics into sd in place
+    _, pre_cal = preprocessed(dict(cfg, size=256, batch=2))
+    with torch.no_grad():
+        orc.generate_fake(sd, orc.default_opt(crop_size=256, isTrain=True), pre_cal, True, rng_k=13, momentum=1.0)
+    assert float(sd["up_3.norm_0.param_free_norm.running_var"].mean()) != 1.0
+    opt = make_opt(is_train=False, ngf=64, ndf=64, crop_size=512, add_feat_zeros=True, batchSize=1)
+    model = Pix2PixModel(opt)
+    assert (model.netG.sw, model.netG.sh) == (9, 9)
+    model.netG.load_state_dict(sd, strict=True)
+    model.eval()
+    data = synthetic_batch(1, 512, 13)
+    out = model(dict(data), mode="inference")
+    assert tuple(out.shape) == (1, 3, 576, 576)
+    _, pre = preprocessed(cfg)
+    oopt = orc.default_opt(isTrain=False, add_feat_zeros=True)
+    with torch.no_grad():
+        ref = orc.generate_fake(sd, oopt, pre, False)
+    mx, mn = max_mean_abs(out, ref)
+    print("G 576x576 (--add_feat_zeros) eval vs oracle: max-abs %.3e mean-abs %.3e" % (mx, mn))
     assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
 
 

@@ -315,7 +315,7 @@ def test_bench_reference_arm_json_contract(monkeypatch, capsys):
     bench = importlib.util.module_from_spec(spec)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"])
     spec.loader.exec_module(bench)
-    monkeypatch.setattr(bench, "cpu_generator_forward_ips", lambda steps, warm, n: (0.25, 4000.0, 16))
+    monkeypatch.setattr(bench, "cpu_reference_ips", lambda steps, warm, train=False: (0.25, 4000.0, 0.05 if train else None, 16, "reference"))
     monkeypatch.delenv("RANK", raising=False)
     bench.run_reference_arm(bench.parse())
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
@@ -325,7 +325,8 @@ def test_bench_reference_arm_json_contract(monkeypatch, capsys):
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 16 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 16 and "workload" in d["config"]
+    assert d["train_step"]["unit"] == "images/s" and d["train_step"]["value"] == 0.05
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # ranks other than 0 print nothing
     monkeypatch.setenv("RANK", "1")
