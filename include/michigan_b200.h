@@ -295,6 +295,22 @@ int mg_unpack_wgrad_gb(const float* dw_packed, float* dwg, float* dwb, int C, in
  * [N,H+2p,W+2p,32] with zero channel padding and reflection padding p: operand of mg_conv_wgrad for the thin convs. */
 int mg_pad_channels32(const float* in, float* out, int N, int H, int W, int CinP, int seg_resize, int reflect_pad, void* stream);
 
+/* ---- adversarial loss reductions (models/networks/loss.py:19-140 GANLoss hinge, 144-175 GANFeatLoss) ------------------
+ * mg_edge_weight: the wide-edge weight map of one discriminator scale (loss.py:60-78): label [N,H,W] (hair mask, 0/1)
+ * -> out [N,h,w] = edges*wide_edge + (1-edges), edges = nearest-resized (maxpool_k - minpool_k) of the nearest-resized
+ * label, k = max(1, int(0.06*h)), pad k/2 (pooled maps are h+1 wide for even k, resized back as the reference does). */
+int mg_edge_weight(const float* label, float* out, int N, int H, int W, int h, int w, float wide_edge, void* stream);
+/* One launch for all terms of a loss evaluation.  terms_dev: device array of n_terms records of mg_loss_term_bytes()
+ * bytes each, layout {const float* a; const float* b; float* ga; long long n; float scale, sign; int op, out_slot;}:
+ *   slots[out_slot] += scale * sum_i f(a_i, b_i)   (fp64 accumulation; caller zeroes `slots`)
+ *   op 0: f = min(sign*a - 1, 0) * (b ? b_i : 1)   hinge, discriminator side (b = weight map)     loss.py:104-120
+ *   op 1: f = a                                    generator hinge -mean(D(fake))                  loss.py:123-124
+ *   op 2: f = |a - b|                              feature matching, b detached                    loss.py:170-172
+ * mg_loss_reduce_bwd writes ga_i = gslots[out_slot] * scale * df/da for every term with ga != null. */
+int mg_loss_reduce(const void* terms_dev, int n_terms, double* slots, void* stream);
+int mg_loss_reduce_bwd(const void* terms_dev, int n_terms, const float* gslots, void* stream);
+int mg_loss_term_bytes(void);
+
 /* ---- data-parallel exchange over NVLink peer memory --------------------------------------------------------
  * One-shot all-reduce (sum, in place) of a small fp64 vector: replaces the SyncBN master/slave message passing of
  * sync_batchnorm/comm.py:49-133 + batchnorm.py:105-126 (ReduceAddCoalesced / Broadcast of [sum | sum of squares]).

@@ -109,6 +109,10 @@ SIGNATURES = {
     "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_edge_weight": [_p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "mg_loss_reduce": [_p, _i, _p, _p],
+    "mg_loss_reduce_bwd": [_p, _i, _p, _p],
+    "mg_loss_term_bytes": [],
     "mg_peer_buffer_bytes": [_i],
     "mg_peer_max_elems": [],
     "mg_peer_allreduce_f64": [_p, _i, _p, _i, _i, C.c_ulonglong, _i, _d, _p, _p],

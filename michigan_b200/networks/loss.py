@@ -1,9 +1,108 @@
 """Hinge GAN loss and GAN feature-matching loss with the reference's call signatures
-(models/networks/loss.py:19-140, 144-175; the in-scope modes: gan_mode='hinge',
-remove_background=False).  These are small reductions over the discriminator's outputs."""
+(models/networks/loss.py:19-140 `GANLoss`, 144-175 `GANFeatLoss`; in-scope modes: gan_mode='hinge',
+remove_background=False), evaluated by the fused reduction kernels of csrc/mg_loss.cu:
+
+  * every call = ONE forward launch (all discriminator scales / all eight feature terms through a descriptor table,
+    fp64 accumulation) and ONE backward launch, instead of ~10 eager ops per scale and per term;
+  * the wide-edge weight map (loss.py:60-78) is one kernel per scale, cached per (label, size) within an iteration.
+"""
+import ctypes as C
+
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
+
+from .. import _lib, ops
+
+
+class _Term(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("ga", C.c_void_p), ("n", C.c_longlong), ("scale", C.c_float),
+                ("sign", C.c_float), ("op", C.c_int32), ("out_slot", C.c_int32)]
+
+
+OP_HINGE_D, OP_SUM, OP_L1 = 0, 1, 2
+_table_cache = {}
+
+
+def _dense(t):
+    """A tensor whose elements occupy one contiguous block (any permutation of strides) or a contiguous copy."""
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
+        return t
+    return t.contiguous()
+
+
+def _device_table(terms, device):
+    """ctypes term records -> device buffer (cached: the caching allocator hands the same addresses back every iteration)."""
+    raw = bytes((_Term * len(terms))(*terms))
+    hit = _table_cache.get(raw)
+    if hit is not None and hit.device == device:
+        return hit
+    if len(_table_cache) > 256:
+        _table_cache.clear()
+    buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    _table_cache[raw] = buf
+    return buf
+
+
+class _LossFn(torch.autograd.Function):
+    """spec: list of (op, a_index, b_tensor_or_None, scale, sign, slot); tensors: the differentiable `a` inputs."""
+
+    @staticmethod
+    def forward(ctx, spec, nslots, *tensors):
+        assert _lib.load().mg_loss_term_bytes() == C.sizeof(_Term)
+        dense = [_dense(t.detach()) for t in tensors]
+        dev = dense[0].device
+        terms = []
+        keep = []
+        for op, ai, b, scale, sign, slot in spec:
+            a = dense[ai]
+            bb = _dense(b.detach()) if b is not None else None
+            if bb is not None:
+                assert bb.numel() == a.numel(), (bb.shape, a.shape)
+                keep.append(bb)
+            terms.append(_Term(a.data_ptr(), bb.data_ptr() if bb is not None else None, None, a.numel(), float(scale), float(sign), op, slot))
+        slots = torch.zeros(nslots, device=dev, dtype=torch.float64)
+        table = _device_table(terms, dev)
+        _lib.check(_lib.load().mg_loss_reduce(table.data_ptr(), len(terms), slots.data_ptr(), ops._stream()), "mg_loss_reduce")
+        ctx.spec, ctx.dense, ctx.keep, ctx.nslots = spec, dense, keep, nslots
+        ctx.shapes = [(t.shape, t.stride(), d.stride()) for t, d in zip(tensors, dense)]
+        return slots.float()
+
+    @staticmethod
+    def backward(ctx, gslots):
+        dense = ctx.dense
+        dev = dense[0].device
+        # one flat buffer for every gradient; a tensor that appears in several terms (never the case for these losses)
+        # would need accumulation - guarded below
+        offs, total = [], 0
+        for d in dense:
+            offs.append(total)
+            total += d.numel()
+        flat = torch.empty(total, device=dev, dtype=torch.float32)
+        seen = set()
+        terms = []
+        for (op, ai, b, scale, sign, slot), kb in zip(ctx.spec, _iter_keep(ctx.spec, ctx.keep)):
+            if ai in seen:
+                raise RuntimeError("a tensor may appear in one loss term only")
+            seen.add(ai)
+            a = dense[ai]
+            terms.append(_Term(a.data_ptr(), kb.data_ptr() if kb is not None else None, flat.data_ptr() + 4 * offs[ai], a.numel(),
+                               float(scale), float(sign), op, slot))
+        table = _device_table(terms, dev)
+        g = gslots.contiguous().float()
+        _lib.check(_lib.load().mg_loss_reduce_bwd(table.data_ptr(), len(terms), g.data_ptr(), ops._stream()), "mg_loss_reduce_bwd")
+        grads = []
+        for i, (shape, stride, dstride) in enumerate(ctx.shapes):
+            if i not in seen:
+                grads.append(None)
+                continue
+            grads.append(torch.as_strided(flat, shape, dstride, offs[i]))
+        return (None, None) + tuple(grads)
+
+
+def _iter_keep(spec, keep):
+    it = iter(keep)
+    for op, ai, b, scale, sign, slot in spec:
+        yield next(it) if b is not None else None
 
 
 class GANLoss(nn.Module):
@@ -15,41 +114,40 @@ class GANLoss(nn.Module):
             raise NotImplementedError("michigan_b200: --remove_background is not implemented")
         self.gan_mode = gan_mode
         self.opt = opt
-
-    def get_wide_edges(self, t, th=0.06):
-        n, c, h, w = t.size()
-        k = max(1, int(h * th))
-        p = int(k / 2)
-        out = F.max_pool2d(t, kernel_size=k, stride=1, padding=p)
-        out2 = 1 - F.max_pool2d(1 - t, kernel_size=k, stride=1, padding=p)
-        return F.interpolate(out - out2, size=(h, w), mode="nearest")
+        self._wcache = {}
 
     def get_weight_mask(self, input, mask):
-        n, c, h, w = input.size()
-        label = F.interpolate(mask, size=(h, w), mode="nearest")
-        edges = self.get_wide_edges(label)
-        return edges * self.opt.wide_edge + (1 - edges)
-
-    def loss(self, input, target_is_real, for_discriminator=True, label=None):
-        if for_discriminator:
-            minval = torch.clamp((input - 1) if target_is_real else (-input - 1), max=0)
-            if self.opt.wide_edge > 1.0:
-                minval = minval * self.get_weight_mask(input, label)
-            return -torch.mean(minval)
-        assert target_is_real, "The generator's hinge loss must be aiming for real"
-        return -torch.mean(input)
+        """loss.py:68-78: edges*wide_edge + (1-edges) at the logits' resolution, [N,h,w] (cached per label / size)."""
+        n, _, h, w = input.shape
+        m = mask.detach()
+        key = (m.data_ptr(), m._version, tuple(m.shape), h, w)
+        hit = self._wcache.get(key)
+        if hit is not None:
+            return hit
+        m3 = m.reshape(m.shape[0], m.shape[-2], m.shape[-1]).contiguous().float()
+        out = torch.empty((n, h, w), device=input.device, dtype=torch.float32)
+        _lib.check(_lib.load().mg_edge_weight(m3.data_ptr(), out.data_ptr(), n, m3.shape[1], m3.shape[2], h, w,
+                                              float(self.opt.wide_edge), ops._stream()), "mg_edge_weight")
+        if len(self._wcache) > 8:
+            self._wcache.clear()
+        self._wcache[key] = out
+        return out
 
     def __call__(self, input, target_is_real, for_discriminator=True, label=None):
-        if isinstance(input, list):
-            loss = 0
-            for pred_i in input:
-                if isinstance(pred_i, list):
-                    pred_i = pred_i[-1]
-                loss_tensor = self.loss(pred_i, target_is_real, for_discriminator, label.detach())
-                bs = 1 if len(loss_tensor.size()) == 0 else loss_tensor.size(0)
-                loss = loss + torch.mean(loss_tensor.view(bs, -1), dim=1)
-            return loss / len(input)
-        return self.loss(input, target_is_real, for_discriminator, label.detach())
+        """loss.py:126-140: list over discriminators (each possibly a list of features, the logits last) -> mean over
+        discriminators of the per-scale loss, a [1] tensor."""
+        preds = input if isinstance(input, list) else [input]
+        logits = [(p[-1] if isinstance(p, list) else p) for p in preds]
+        num = len(logits)
+        spec = []
+        for i, x in enumerate(logits):
+            if for_discriminator:
+                wmap = self.get_weight_mask(x, label) if self.opt.wide_edge > 1.0 else None
+                spec.append((OP_HINGE_D, i, wmap, -1.0 / (x.numel() * num), 1.0 if target_is_real else -1.0, 0))
+            else:
+                assert target_is_real, "The generator's hinge loss must be aiming for real"
+                spec.append((OP_SUM, i, None, -1.0 / (x.numel() * num), 1.0, 0))
+        return _LossFn.apply(spec, 1, *logits)
 
 
 class GANFeatLoss(nn.Module):
@@ -58,9 +156,17 @@ class GANFeatLoss(nn.Module):
         self.opt = opt
 
     def forward(self, pred_fake, pred_real, label=None):
+        """loss.py:163-175: sum over discriminators and their intermediate features of L1(fake, real.detach()) * lambda_feat / num_D."""
         num_D = len(pred_fake)
-        total = torch.zeros(1, device=pred_fake[0][0].device)
+        spec, tensors = [], []
         for i in range(num_D):
             for j in range(len(pred_fake[i]) - 1):
-                total = total + F.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) * self.opt.lambda_feat / num_D
-        return total
+                f, r = pred_fake[i][j], pred_real[i][j].detach()
+                fd = _dense(f)
+                rd = _dense(r)
+                if fd.stride() != rd.stride():
+                    rd = r.contiguous()
+                    fd = f.contiguous()
+                spec.append((OP_L1, len(tensors), rd, self.opt.lambda_feat / (num_D * f.numel()), 1.0, 0))
+                tensors.append(fd)
+        return _LossFn.apply(spec, 1, *tensors)

@@ -249,3 +249,60 @@ def test_igemm_dual_pipelines_n256(gen, fmt):
             _lib_mod().set_tuning("MG_DUAL", prev_knob)
         assert rel_err(nchw(outs[dual]), ref) <= tol, dual
     assert torch.equal(outs["2"], outs["0"])
+
+
+def test_fused_loss_reductions_vs_reference_formulas(gen):
+    """GANLoss (hinge, wide-edge weights, loss.py:60-140) and GANFeatLoss (loss.py:163-175) on the fused reduction kernels
+    against the oracle's restatement of the reference formulas, values and gradients, at the discriminator's odd output
+    sizes (67/35: even and odd pooling windows) and with channels-last feature slices as the discriminator produces them."""
+    import michigan_oracle as orc
+    from michigan_b200.networks.loss import GANFeatLoss, GANLoss
+    from michigan_b200.options import make_opt
+    opt = make_opt()
+    oopt = orc.default_opt()
+    N = 3
+    label = torch.zeros(N, 1, 512, 512)
+    label[:, :, 100:300, 120:400] = 1.0
+    label[1, :, 50:90, 30:500] = 1.0
+    sizes = [(67, 64), (35, 128)]
+
+    def make(requires_grad):
+        outs = []
+        for h, c in sizes:
+            feats = [torch.randn(2 * N, h, h, cc, generator=gen).permute(0, 3, 1, 2) for cc in (c, c)]
+            outs.append(feats + [torch.randn(2 * N, h, h, 1, generator=gen).permute(0, 3, 1, 2) * 2])
+        return outs
+
+    cpu = make(True)
+    ref_in = [[t.clone().requires_grad_(True) for t in o] for o in cpu]
+    dev_in = [[t.clone().to(dev).requires_grad_(True) for t in o] for o in cpu]
+
+    def halves(outs):
+        return [[t[:N] for t in o] for o in outs], [[t[N:] for t in o] for o in outs]
+
+    crit, critF = GANLoss("hinge", opt=opt), GANFeatLoss(opt)
+    for name in ("d_fake", "d_real", "g", "feat"):
+        rf, rr = halves(ref_in)
+        df, dr = halves(dev_in)
+        if name == "d_fake":
+            ref, got = orc.gan_loss_hinge(rf, False, True, label, oopt), crit(df, False, for_discriminator=True, label=label.to(dev))
+        elif name == "d_real":
+            ref, got = orc.gan_loss_hinge(rr, True, True, label, oopt), crit(dr, True, for_discriminator=True, label=label.to(dev))
+        elif name == "g":
+            ref, got = orc.gan_loss_hinge(rf, True, False, label, oopt), crit(df, True, for_discriminator=False, label=label.to(dev))
+        else:
+            ref, got = orc.gan_feat_loss(rf, rr, oopt), critF(df, dr, label.to(dev))
+        assert got.shape == (1,)
+        assert abs(float(got) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (name, float(got), float(ref))
+        for o in ref_in + dev_in:
+            for t in o:
+                t.grad = None
+        (ref.sum() * 1.7).backward()
+        (got.sum() * 1.7).backward()
+        for ro, do in zip(ref_in, dev_in):
+            for rt, dt in zip(ro, do):
+                if rt.grad is None:
+                    assert dt.grad is None or float(dt.grad.abs().max()) == 0.0
+                else:
+                    assert dt.grad is not None, name
+                    assert (dt.grad.cpu() - rt.grad).abs().max().item() <= 1e-6 * max(1.0, rt.grad.abs().max().item()), name
