@@ -29,6 +29,7 @@ enum TuneKnob {
     TK_WGRAD_DUAL,       // MG_WGRAD_DUAL (default 1)
     TK_THIN_GEMM,        // MG_THIN_GEMM (default 1)
     TK_THIN_WGRAD_LEGACY,// MG_THIN_WGRAD_LEGACY (default 0)
+    TK_GROUP3,           // MG_GROUP3: 3x3/s1 convs on the halo-patch + M-tile-group kernel (mg_conv3x3.cu): 0 off, 1 thin N, 2 all
     TK_COUNT
 };
 int tune(int knob);
@@ -44,6 +45,10 @@ int probe_bits();   // env MG_DBG, read once
 #define MG_DBGV(p) 0
 #define MG_PROFV(p) 0
 #endif
+
+struct IgemmParams;
+// mg_conv3x3.cu: 1 = launched, 0 = shape not eligible (use the per-tap kernel), anything else = error status
+int conv3x3_group_launch(const mg_igemm_args* a, IgemmParams& p, int BN, int cw, int scratch_bytes, int spec, cudaStream_t stream);
 
 inline int check_launch(const char* what) {
     count_launch();

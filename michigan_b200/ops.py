@@ -41,7 +41,8 @@ def _p(t):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream (the C accessor: ~0.3 us instead of ~14 us for the Stream object)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _chk(t, name, dtype=torch.float32):

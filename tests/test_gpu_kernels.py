@@ -306,3 +306,71 @@ def test_fused_loss_reductions_vs_reference_formulas(gen):
                 else:
                     assert dt.grad is not None, name
                     assert (dt.grad.cpu() - rt.grad).abs().max().item() <= 1e-6 * max(1.0, rt.grad.abs().max().item()), name
+
+
+@pytest.mark.parametrize("fmt,Cin,Cout,h,w", [("tf32", 64, 64, 48, 32), ("tf32", 32, 256, 40, 64), ("f16", 128, 128, 32, 32),
+                                              ("bf3", 128, 64, 40, 48), ("bf3", 64, 128, 32, 32), ("bf3", 64, 256, 32, 32)])
+def test_conv3x3_group_kernel_matches_per_tap_kernel(gen, fmt, Cin, Cout, h, w):
+    """mg_conv3x3.cu (halo patches shared by two M tiles, one MMA-issuing thread per M tile) against the per-tap kernel and
+    against torch, for every operand format and accumulator arrangement: TF32 (4 / 1x2 accumulators), fp16, bf16 hi+lo
+    merged (Cout <= 128) and 3-pass (Cout 256); heights that are not a multiple of the 16-row tile; max_ctas forces several
+    groups per CTA (ring wrap-around, accumulator double buffering)."""
+    ops = _ops()
+    N = 2
+    x = torch.randn(N, Cin, h, w, generator=gen).to(dev)
+    wt = (torch.randn(Cout, Cin, 3, 3, generator=gen) / (3 * Cin ** 0.5)).to(dev)
+    b = torch.randn(Cout, generator=gen).to(dev)
+    res = torch.randn(N, h, w, Cout, generator=gen).to(dev)
+
+    def run():
+        if fmt == "tf32":
+            xt, wq = tf32_trunc(x), tf32_trunc(wt)
+            return ops.conv_igemm(nhwc(xt), ops.pack_weight(wq, None, round_tf32=True), Cout, 3, 3, 1, 1, bias=b, res=res, act=2, max_ctas=5), \
+                F.leaky_relu(F.conv2d(xt, wq, b, padding=1) + nchw(res), 0.2), 2e-5
+        if fmt == "f16":
+            return ops.conv_igemm(nhwc(x).half(), ops.pack_weight16(wt, None, ops.F16, split=False), Cout, 3, 3, 1, 1, bias=b, res=res, act=2,
+                                  a_fmt=ops.F16, max_ctas=5), \
+                F.leaky_relu(F.conv2d(x.half().float(), wt.half().float(), b, padding=1) + nchw(res), 0.2), 2e-5
+        xn = nhwc(x)
+        hi = xn.bfloat16()
+        lo = (xn - hi.float()).bfloat16()
+        return ops.conv_igemm(hi, ops.pack_weight16(wt, None, ops.BF16, split=True), Cout, 3, 3, 1, 1, bias=b, res=res, act=2, a_fmt=ops.BF16,
+                              x_lo=lo, max_ctas=5), F.leaky_relu(F.conv2d(x, wt, b, padding=1) + nchw(res), 0.2), 6e-5
+
+    outs = {}
+    for g3 in (2, 0):
+        prev = _lib_mod().set_tuning("MG_GROUP3", g3)
+        try:
+            outs[g3], ref, tol = run()
+        finally:
+            _lib_mod().set_tuning("MG_GROUP3", prev)
+        assert rel_err(nchw(outs[g3]), ref) <= tol, (g3, rel_err(nchw(outs[g3]), ref))
+    assert rel_err(outs[2], outs[0]) <= 2e-6
+
+
+def test_conv3x3_group_kernel_spade_epilogue(gen):
+    """The fused SPADE gamma|beta GEMM (fp16 operands, bf16 hi/lo output, folded 2x upsample of x) through the group kernel."""
+    ops = _ops()
+    N, C, h = 2, 64, 32
+    actv = torch.randn(N, h, h, 128, generator=gen).to(dev)
+    wg = (torch.randn(C, 128, 3, 3, generator=gen) / 34).to(dev)
+    wb = (torch.randn(C, 128, 3, 3, generator=gen) / 34).to(dev)
+    xs = torch.randn(N, h // 2, h // 2, C, generator=gen).to(dev)
+    ns, nh, g1, bb = [torch.randn(C, generator=gen).to(dev) for _ in range(4)]
+    wp = ops.pack_weight_gb16(wg, wb)
+    outs = {}
+    for g3 in (2, 0):
+        prev = _lib_mod().set_tuning("MG_GROUP3", g3)
+        try:
+            _, hi, lo = ops.conv_igemm(actv.half(), wp, C, 3, 3, 1, 1, act=2, a_fmt=ops.F16, spade=(xs, 1, ns, nh, g1, bb),
+                                       out16=(ops.BF16, True), want_f32=False, max_ctas=3)
+            outs[g3] = hi.float() + lo.float()
+        finally:
+            _lib_mod().set_tuning("MG_GROUP3", prev)
+    a16 = nchw(actv.half().float())
+    gamma = F.conv2d(a16, wg.half().float(), None, padding=1)
+    beta = F.conv2d(a16, wb.half().float(), None, padding=1)
+    xh = F.interpolate(nchw(xs), scale_factor=2, mode="nearest") * ns.view(1, -1, 1, 1) + nh.view(1, -1, 1, 1)
+    ref = F.leaky_relu(xh * (g1.view(1, -1, 1, 1) + gamma) + (bb.view(1, -1, 1, 1) + beta), 0.2)
+    assert rel_err(nchw(outs[2]), ref) <= 1e-4 and rel_err(nchw(outs[0]), ref) <= 1e-4
+    assert rel_err(outs[2], outs[0]) <= 2e-5
