@@ -295,6 +295,18 @@ int mg_unpack_wgrad_gb(const float* dw_packed, float* dwg, float* dwb, int C, in
  * [N,H+2p,W+2p,32] with zero channel padding and reflection padding p: operand of mg_conv_wgrad for the thin convs. */
 int mg_pad_channels32(const float* in, float* out, int N, int H, int W, int CinP, int seg_resize, int reflect_pad, void* stream);
 
+/* ---- input-pipeline prologue (data/base_dataset.py:335-396; per-sample CPU work of Dataset.__getitem__ in the reference) -----
+ * mg_noise_pyramid: generate_noise (base_dataset.py:387-396): out[n,c,y,x] = mean over octaves l of cv2.resize(field_l, (H,W),
+ *   INTER_LINEAR)[y,x,c]; fields: HOST array of `levels` device pointers, octave l = [N, H>>l, W>>l, 3] draws of N(0.5, 0.25^2).
+ * mg_orient_rgb: trans_orient_to_rgb + ToTensor (base_dataset.py:363-385,107-110): orient [N,H,W] (0..255), label [N,H,W] ->
+ *   [N,3,H,W] = uint8([(cos2t+1)/2, (sin2t+1)/2, 0.5] * label * 255) / 255 * label, t = orient/255*pi.
+ * mg_hole_mask: generate_hole (base_dataset.py:335-361) for a batch: th_u[n] in [0.5,1.2] and idx_u[n] in [0,1) replace
+ *   random.uniform / random.randint; centre = the floor(idx_u*count)-th nonzero pixel of orient_mask in row-major order. */
+int mg_noise_pyramid(const float* const* fields, int levels, float* out_nchw, int N, int H, int W, void* stream);
+int mg_orient_rgb(const float* orient, const float* label, float* out_nchw, int N, int H, int W, void* stream);
+int mg_hole_mask(const float* mask, const float* orient_mask, const float* th_u, const float* idx_u, float* hole, int N, int H, int W,
+                 void* stream);
+
 /* ---- adversarial loss reductions (models/networks/loss.py:19-140 GANLoss hinge, 144-175 GANFeatLoss) ------------------
  * mg_edge_weight: the wide-edge weight map of one discriminator scale (loss.py:60-78): label [N,H,W] (hair mask, 0/1)
  * -> out [N,h,w] = edges*wide_edge + (1-edges), edges = nearest-resized (maxpool_k - minpool_k) of the nearest-resized

@@ -2,6 +2,7 @@
 // Hand-written inline PTX; no CUTLASS/CuTe dependency.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace mg {

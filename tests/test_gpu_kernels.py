@@ -374,3 +374,62 @@ def test_conv3x3_group_kernel_spade_epilogue(gen):
     ref = F.leaky_relu(xh * (g1.view(1, -1, 1, 1) + gamma) + (bb.view(1, -1, 1, 1) + beta), 0.2)
     assert rel_err(nchw(outs[2]), ref) <= 1e-4 and rel_err(nchw(outs[0]), ref) <= 1e-4
     assert rel_err(outs[2], outs[0]) <= 2e-5
+
+
+def test_input_prologue_kernels_vs_reference_formulas(gen):
+    """The GPU input prologue (noise pyramid, orientation RGB, hole mask) against numpy/cv2 restatements of the reference's
+    per-sample CPU functions (data/base_dataset.py:335-396) on identical random draws."""
+    import math
+    import cv2
+    import numpy as np
+    from michigan_b200 import prologue
+    n, h, w = 2, 64, 64
+    rs = np.random.RandomState(3)
+    fields = [rs.normal(loc=0.5, scale=0.25, size=(n, hh, ww, 3)).astype(np.float32) for hh, ww in prologue.noise_octave_sizes(h, w)]
+    assert len(fields) == 4
+    ref = np.zeros((n, h, w, 3), np.float32)
+    for i in range(n):
+        acc = np.zeros((h, w, 3), np.float32)
+        for f in fields:
+            acc += cv2.resize(f[i].astype(np.float64), dsize=(h, w))          # generate_noise: float64 draws, INTER_LINEAR
+        ref[i] = acc / len(fields)
+    got = prologue.noise_from_fields([torch.from_numpy(f).to(dev) for f in fields], n, h, w)
+    assert (got.cpu() - torch.from_numpy(ref).permute(0, 3, 1, 2)).abs().max().item() <= 2e-6
+    assert abs(float(prologue.generate_noise(2, 128, 128, dev).mean()) - 0.5) < 0.02
+
+    orient = torch.floor(torch.rand(n, 1, h, w, generator=gen) * 255)
+    label = (torch.rand(n, 1, h, w, generator=gen) > 0.4).float()
+    exp = torch.zeros(n, 3, h, w)
+    for i in range(n):
+        om = orient[i, 0].numpy().astype(np.float64) / 255.0 * math.pi
+        rgb = np.zeros((h, w, 3))
+        rgb[..., 1] = (np.sin(2 * om) + 1) / 2
+        rgb[..., 0] = (np.cos(2 * om) + 1) / 2
+        rgb[..., 2] = 0.5
+        rgb *= label[i, 0].numpy()[..., np.newaxis]
+        q = np.uint8(rgb * 255.0).astype(np.float32) / 255.0                 # PIL image -> ToTensor
+        exp[i] = torch.from_numpy(q).permute(2, 0, 1) * label[i]
+    got = prologue.orient_rgb(orient.to(dev), label.to(dev)).cpu()
+    # cos/sin in double on both sides; a product landing within 1 ulp of an integer may truncate differently
+    diff = (got - exp).abs()
+    assert (diff > 1e-6).float().mean().item() < 1e-3 and diff.max().item() <= 1.0 / 255 + 1e-6
+
+    mask = torch.zeros(n, 1, h, w)
+    mask[:, :, 10:50, 12:40] = 1
+    omask = mask.clone()
+    omask[:, :, 10:20] = 0
+    omask[1] = 0                                                              # empty orientation mask: returned as is
+    th_u = torch.tensor([0.9, 0.7])
+    idx_u = torch.tensor([0.37, 0.5])
+    got = prologue.hole_mask(mask.to(dev), omask.to(dev), th_u.to(dev), idx_u.to(dev)).cpu()
+    om0 = omask[0, 0].numpy()
+    coord = np.where(om0 != 0)
+    nums = len(coord[0])
+    rr = int(int(0.9 * nums) / math.pi)
+    k = min(int(math.floor(np.float32(0.37) * np.float32(nums))), nums - 1)
+    cy, cx = coord[0][k], coord[1][k]
+    yy, xx = np.mgrid[0:h, 0:w]
+    tmp = (((yy - cy) ** 2 + (xx - cx) ** 2) < rr).astype(np.float32)
+    exp0 = om0 * tmp + (mask[0, 0].numpy() - om0)
+    assert np.array_equal(got[0, 0].numpy(), exp0)
+    assert torch.equal(got[1], omask[1])
