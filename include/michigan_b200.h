@@ -323,6 +323,19 @@ int mg_loss_reduce(const void* terms_dev, int n_terms, double* slots, void* stre
 int mg_loss_reduce_bwd(const void* terms_dev, int n_terms, const float* gslots, void* stream);
 int mg_loss_term_bytes(void);
 
+/* ---- Gabor orientation loss (models/networks/loss.py:274-385 L1OLoss, orient_filter 'gabor') --------------------------------
+ * img [N,3,H,W] in [-1,1]; bank [17*17][32] = the 32 Gabor kernels of gabor_fn (loss.py:214-240), filter index fastest;
+ * label2 [N,2,H,W] = (sin 2t, cos 2t) of the target orientation; hair [N,H,W].
+ * fwd: sums[0] += sum |orient_fake*hair - label2*hair| (both channels), sums[1] += sum log(clamp(conf,.001,1))*hair,
+ *      sums[2] += sum hair  (fp64, caller zeroes);  => orient_loss = sums[0] / (2*N*H*W), confidence_loss = -sums[1] / sums[2];
+ *      per pixel: winning filter index and d sums[0] / d max-response, d sums[1] / d max-response.
+ * bwd: dimg = d(w[0]*sums[0] + w[1]*sums[1]) / d img, weights2 = device [2] floats (the upstream gradients folded with the
+ *      normalisations above). */
+int mg_orient_loss_fwd(const float* img_nchw, const float* bank, const float* label2, const float* hair, unsigned char* idx, float* dmax_l1,
+                       float* dmax_log, double* sums, int N, int H, int W, void* stream);
+int mg_orient_loss_bwd(const float* bank, const unsigned char* idx, const float* dmax_l1, const float* dmax_log, const float* weights2,
+                       float* dimg_nchw, int N, int H, int W, void* stream);
+
 /* ---- data-parallel exchange over NVLink peer memory --------------------------------------------------------
  * One-shot all-reduce (sum, in place) of a small fp64 vector: replaces the SyncBN master/slave message passing of
  * sync_batchnorm/comm.py:49-133 + batchnorm.py:105-126 (ReduceAddCoalesced / Broadcast of [sum | sum of squares]).

@@ -112,6 +112,8 @@ SIGNATURES = {
     "mg_noise_pyramid": [_p, _i, _p, _i, _i, _i, _p],
     "mg_orient_rgb": [_p, _p, _p, _i, _i, _i, _p],
     "mg_hole_mask": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "mg_orient_loss_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "mg_orient_loss_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mg_edge_weight": [_p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mg_loss_reduce": [_p, _i, _p, _p],
     "mg_loss_reduce_bwd": [_p, _i, _p, _p],

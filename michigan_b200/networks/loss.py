@@ -170,3 +170,74 @@ class GANFeatLoss(nn.Module):
                 spec.append((OP_L1, len(tensors), rd, self.opt.lambda_feat / (num_D * f.numel()), 1.0, 0))
                 tensors.append(fd)
         return _LossFn.apply(spec, 1, *tensors)
+
+
+# ================================================================================================ Gabor orientation loss
+def gabor_bank(device, num_kernels=32, kernel_size=17):
+    """The 32 Gabor kernels the reference rebuilds on every call (gabor_fn, loss.py:214-240; sigma_x 2, sigma_y 3, lambda 4,
+    psi 0, theta_k = pi*k/32), with the same float32 torch arithmetic, laid out [17*17][32] for the fused kernel."""
+    import math
+    r = kernel_size // 2
+    y = torch.arange(-r, r + 1, device=device).view(1, -1).repeat(kernel_size, 1).float()       # varies along columns
+    x = torch.arange(-r, r + 1, device=device).view(-1, 1).repeat(1, kernel_size).float()       # varies along rows
+    ks = []
+    for k in range(num_kernels):
+        theta = torch.ones(1, device=device) * (math.pi * k / num_kernels)
+        x_t = x * torch.cos(theta) + y * torch.sin(theta)
+        y_t = -x * torch.sin(theta) + y * torch.cos(theta)
+        ks.append(torch.exp(-.5 * (x_t ** 2 / 2.0 ** 2 + y_t ** 2 / 3.0 ** 2)) * torch.cos(2 * math.pi / 4.0 * x_t + 0.0))
+    return torch.stack(ks, dim=-1).reshape(kernel_size * kernel_size, num_kernels).contiguous()
+
+
+class _OrientLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, bank, label2, hair):
+        n, _, h, w = img.shape
+        dev = img.device
+        img_c = img.detach().contiguous()
+        idx = torch.empty((n, h, w), device=dev, dtype=torch.uint8)
+        d1 = torch.empty((n, h, w), device=dev, dtype=torch.float32)
+        d2 = torch.empty((n, h, w), device=dev, dtype=torch.float32)
+        sums = torch.zeros(3, device=dev, dtype=torch.float64)
+        _lib.check(_lib.load().mg_orient_loss_fwd(img_c.data_ptr(), bank.data_ptr(), label2.data_ptr(), hair.data_ptr(), idx.data_ptr(),
+                                                  d1.data_ptr(), d2.data_ptr(), sums.data_ptr(), n, h, w, ops._stream()), "mg_orient_loss_fwd")
+        ctx.save_for_backward(bank, idx, d1, d2, sums)
+        ctx.shape = (n, h, w)
+        orient = (sums[0] / (2.0 * n * h * w)).float().reshape(())
+        conf = (-sums[1] / sums[2]).float().reshape(())
+        return orient, conf
+
+    @staticmethod
+    def backward(ctx, g_orient, g_conf):
+        bank, idx, d1, d2, sums = ctx.saved_tensors
+        n, h, w = ctx.shape
+        wts = torch.stack([g_orient.double() / (2.0 * n * h * w), -g_conf.double() / sums[2]]).float().contiguous()
+        dimg = torch.empty((n, 3, h, w), device=idx.device, dtype=torch.float32)
+        _lib.check(_lib.load().mg_orient_loss_bwd(bank.data_ptr(), idx.data_ptr(), d1.data_ptr(), d2.data_ptr(), wts.data_ptr(), dimg.data_ptr(),
+                                                  n, h, w, ops._stream()), "mg_orient_loss_bwd")
+        return dimg, None, None, None
+
+
+class L1OLoss(nn.Module):
+    """loss.py:274-385 with orient_filter='gabor': (orient_loss, confidence_loss) = forward(fake_image, orientation_label,
+    input_semantics).  orientation_label: the 1-channel angle map (0..255) or, with --use_ig, the 2-channel (sin 2t, cos 2t) map."""
+
+    def __init__(self, opt, channel_in=1, channel_out=1, stride=1, padding=8):
+        super().__init__()
+        if "gabor" not in getattr(opt, "orient_filter", "gabor"):
+            raise NotImplementedError("michigan_b200: orient_filter '%s' (the DoG variant has no kernel)" % opt.orient_filter)
+        self.opt = opt
+        self._bank = None
+
+    def forward(self, fake_image0, orientation_label0, input_semantics):
+        import math
+        dev = fake_image0.device
+        if self._bank is None or self._bank.device != dev:
+            self._bank = gabor_bank(dev)
+        hair = input_semantics[:, 1].contiguous().float()
+        if not self.opt.use_ig:
+            t = orientation_label0.float() / 255 * math.pi
+            label2 = torch.cat([torch.sin(2 * t), torch.cos(2 * t)], dim=1).contiguous()
+        else:
+            label2 = orientation_label0.float().contiguous()
+        return _OrientLossFn.apply(fake_image0, self._bank, label2.detach(), hair.detach())

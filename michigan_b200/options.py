@@ -24,7 +24,7 @@ def make_opt(is_train=True, **overrides):
         no_ganFeat_loss=False, gan_mode="hinge", no_TTUR=False, lr=0.0002, beta1=0.5, beta2=0.999, wide_edge=2.0,
         # loss switches: the stand-alone model implements hinge GAN + GAN_Feat (SURVEY.md §8d flag set)
         no_vgg_loss=True, no_style_loss=True, no_content_loss=True, no_background_loss=True, no_rgb_loss=True, no_lab_loss=True,
-        no_orient_loss=True, no_confidence_loss=True,
+        no_orient_loss=True, no_confidence_loss=True, orient_filter="gabor", lambda_orient=10.0, lambda_confidence=100.0,
         isTrain=is_train,
     )
     for k, v in overrides.items():

@@ -32,10 +32,11 @@ class Pix2PixModel(torch.nn.Module):
         if opt.isTrain:
             # The reference's generator objective also contains VGG / style / content / background / rgb / lab / orientation
             # terms, all ON by default (pix2pix_model.py:296-345).  This stand-alone model implements the SURVEY §8d loss set
-            # (hinge GAN + GAN feature matching): anything else must be switched off explicitly rather than silently dropped.
+            # (hinge GAN + GAN feature matching) plus the Gabor orientation / confidence loss (loss.py:274-385, --no_orient_loss to
+            # drop it): anything else must be switched off explicitly rather than silently dropped.
             # (Through michigan_b200.install() the reference's own Pix2PixModel computes whatever losses it is asked for.)
             missing = [f for f in ("no_vgg_loss", "no_style_loss", "no_content_loss", "no_background_loss", "no_rgb_loss",
-                                   "no_lab_loss", "no_orient_loss") if not getattr(opt, f, False)]
+                                   "no_lab_loss") if not getattr(opt, f, False)]
             if missing:
                 raise NotImplementedError("michigan_b200.Pix2PixModel trains with the hinge GAN + GAN_Feat losses only; pass --%s "
                                           "(or drive the reference's Pix2PixModel through michigan_b200.install())" % " --".join(missing))
@@ -48,6 +49,9 @@ class Pix2PixModel(torch.nn.Module):
         if opt.isTrain:
             self.criterionGAN = GANLoss(opt.gan_mode, opt=opt)
             self.criterionGANFeat = GANFeatLoss(opt)
+            if not getattr(opt, "no_orient_loss", False):
+                from .networks.loss import L1OLoss
+                self.criterionOrient = L1OLoss(opt)
         if not opt.isTrain or getattr(opt, "continue_train", False):
             self._maybe_load(opt)
 
@@ -180,6 +184,12 @@ class Pix2PixModel(torch.nn.Module):
         ref_is_tag = bool(torch.sum(input_tag[:, 1] - input_ref[:, 1]) == 0)
         if self.opt.curr_step == 1 and not self.opt.no_ganFeat_loss and ref_is_tag:
             G_losses["GAN_Feat"] = self.criterionGANFeat(pred_fake, pred_real, label_tag)
+        if not getattr(self.opt, "no_orient_loss", False):
+            # pix2pix_model.py:340-347
+            orient_loss, confidence_loss = self.criterionOrient(fake_image, orient_mask, input_tag)
+            G_losses["ORIENT"] = orient_loss * self.opt.lambda_orient
+            if not getattr(self.opt, "no_confidence_loss", False):
+                G_losses["CONFIDENCE"] = confidence_loss * self.opt.lambda_confidence
         return G_losses, fake_image
 
     def compute_discriminator_loss(self, input_ref, input_tag, image_ref, image_tag, orient_mask, noise):

@@ -494,3 +494,44 @@ def inpainting_orient(sd_ig, crop_size, hole, orient_rgb, noise, mask):
     o2 = (out[:, :-1] - 0.5) * 2
     orient = torch.stack([o2[:, 1], o2[:, 0]], dim=1) * mask
     return out, orient
+
+
+# ----------------------------------------------------------------------------------------------- Gabor orientation loss
+# SURVEY.md §8f row 2 ("next"), first slice: L1OLoss with orient_filter='gabor' (models/networks/loss.py:214-240 gabor_fn,
+# 274-318 calOrientationGabor, 329-372 forward).  The reference class hard-codes .cuda() (loss.py:218-232,284,297), so on the
+# CPU-only build box it cannot be imported-and-run; tests/test_gpu_orient.py pins this restatement against the reference's own
+# class on the GPU box (baseline/_ref).
+def gabor_kernels(num_kernels=32, kernel_size=17):
+    r = kernel_size // 2
+    y = torch.arange(-r, r + 1).view(1, -1).repeat(kernel_size, 1).float()
+    x = torch.arange(-r, r + 1).view(-1, 1).repeat(1, kernel_size).float()
+    ks = []
+    for k in range(num_kernels):
+        theta = torch.ones(1) * (math.pi * k / num_kernels)
+        x_t = x * torch.cos(theta) + y * torch.sin(theta)
+        y_t = -x * torch.sin(theta) + y * torch.cos(theta)
+        ks.append(torch.exp(-.5 * (x_t ** 2 / 2.0 ** 2 + y_t ** 2 / 3.0 ** 2)) * torch.cos(2 * math.pi / 4.0 * x_t))
+    return torch.stack(ks, 0).unsqueeze(1)          # [32,1,17,17]
+
+
+def orient_loss_gabor(fake_image0, orientation_label0, input_semantics, use_ig=False):
+    """-> (orient_loss, confidence_loss), loss.py:329-372 with 'gabor' in opt.orient_filter."""
+    hair = input_semantics[:, 1:2]
+    fake = (fake_image0 + 1) / 2.0 * 255
+    gray = (0.299 * fake[:, 0] + 0.587 * fake[:, 1] + 0.144 * fake[:, 2]).unsqueeze(1)
+    res = F.conv2d(gray, gabor_kernels().to(gray.dtype), stride=1, padding=8)
+    res = res * (res >= 0).to(res.dtype)                      # resTensor[resTensor < 0] = 0 (in place: zero gradient there)
+    max_idx = torch.argmax(res, dim=1).float()
+    conf = (torch.tanh(torch.max(res, dim=1)[0]) + 1) / 2.0
+    conf = conf.unsqueeze(1)
+    ang = (max_idx * math.pi / 32).unsqueeze(1)
+    two = torch.cat([torch.sin(2 * ang), torch.cos(2 * ang)], dim=1) * conf
+    if not use_ig:
+        lab = orientation_label0 / 255 * math.pi
+        lab2 = torch.cat([torch.sin(2 * lab), torch.cos(2 * lab)], dim=1)
+    else:
+        lab2 = orientation_label0
+    orient_loss = F.l1_loss(two * hair, (lab2 * hair).detach())
+    confc = torch.clamp(conf, 0.001, 1)
+    confidence_loss = -torch.sum(torch.log(confc) * hair) / torch.sum(hair)
+    return orient_loss, confidence_loss
