@@ -321,12 +321,15 @@ def timed_blocks(step, steps, world):
         torch.cuda.synchronize()
 
     blocks = []
+    timed_blocks.host_ms = []          # CPU time to ISSUE each block (no synchronisation inside a block)
     while True:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             step()
+        timed_blocks.host_ms.append((time.perf_counter() - t0) * 1e3)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -480,9 +483,8 @@ def train_step_leg(a, rank, world, local, model):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    t_host0 = time.perf_counter()
     blocks = timed_blocks(step, a.steps, world)
-    host_ms = (time.perf_counter() - t_host0) * 1e3 / (a.steps * len(blocks))
+    host_ms = median(timed_blocks.host_ms) / a.steps
     launches = (_lib.launch_count() - l0) // len(blocks)
     clocks = sampler.stop() if rank == 0 else None
     ms_block = median(blocks)
@@ -528,7 +530,7 @@ def train_step_leg(a, rank, world, local, model):
                 "how": "train_iteration(DataParallelWithCallback(Pix2PixModel), ...) per step from pinned host tensors; the loss "
                        "scalars are copied to pinned host memory and the stream is synchronised every step; wall clock"},
         "gpu_launches": launches, "clocks": clocks, "host_enqueue_ms_per_step": host_ms,
-        "losses": {k: float(v.mean()) for k, v in last["losses"].items()},
+        "losses": {k: float(v.detach().mean()) for k, v in last["losses"].items()},
     }
     return out
 

