@@ -295,6 +295,13 @@ int mg_unpack_wgrad_gb(const float* dw_packed, float* dwg, float* dwb, int C, in
  * [N,H+2p,W+2p,32] with zero channel padding and reflection padding p: operand of mg_conv_wgrad for the thin convs. */
 int mg_pad_channels32(const float* in, float* out, int N, int H, int W, int CinP, int seg_resize, int reflect_pad, void* stream);
 
+/* ---- self-attention of the InpaintGenerator (generator.py:467-485) --------------------------------------------------------
+ * softmax(Q K^T) V runs as two mg_conv_igemm launches per image (1x1 convs whose weight operand is that image's K resp. V^T)
+ * with this row softmax in between: x [rows, cols] scores -> probabilities, written as the operand of the second product:
+ * out32 (optionally TF32-rounded) and / or 16-bit hi (+ lo residual), fmt 1 = fp16, 2 = bf16; any of them may be null. */
+int mg_softmax_rows(const float* x, long long rows, int cols, float* out32, void* out_hi, void* out_lo, int out16_fmt, int round_out,
+                    void* stream);
+
 /* ---- input-pipeline prologue (data/base_dataset.py:335-396; per-sample CPU work of Dataset.__getitem__ in the reference) -----
  * mg_noise_pyramid: generate_noise (base_dataset.py:387-396): out[n,c,y,x] = mean over octaves l of cv2.resize(field_l, (H,W),
  *   INTER_LINEAR)[y,x,c]; fields: HOST array of `levels` device pointers, octave l = [N, H>>l, W>>l, 3] draws of N(0.5, 0.25^2).

@@ -109,6 +109,7 @@ SIGNATURES = {
     "mg_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_maxpool_mask": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mg_avgpool3s2": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "mg_softmax_rows": [_p, _ll, _i, _p, _p, _p, _i, _i, _p],
     "mg_noise_pyramid": [_p, _i, _p, _i, _i, _i, _p],
     "mg_orient_rgb": [_p, _p, _p, _i, _i, _i, _p],
     "mg_hole_mask": [_p, _p, _p, _p, _p, _i, _i, _i, _p],

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmichigan_sm100.so")
-SOURCES = ["mg_api.cu", "mg_igemm.cu", "mg_aux.cu", "mg_wgrad.cu", "mg_bwd.cu", "mg_segconv.cu", "mg_peer.cu", "mg_loss.cu", "mg_conv3x3.cu", "mg_synth.cu", "mg_orient.cu"]  # missing files are skipped
+SOURCES = ["mg_api.cu", "mg_igemm.cu", "mg_aux.cu", "mg_wgrad.cu", "mg_bwd.cu", "mg_segconv.cu", "mg_peer.cu", "mg_loss.cu", "mg_conv3x3.cu", "mg_synth.cu", "mg_orient.cu", "mg_attn.cu"]  # missing files are skipped
 HEADERS = ["mg_ptx.cuh", "mg_internal.h", "mg_epilogue.cuh", os.path.join("..", "..", "include", "michigan_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -88,25 +88,35 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int st = 0; uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)stage_bytes;
-            for (int t = t_begin; t < t_end; ++t) {
-                const int tw = t % p.tiles_w;
-                const int th = (t / p.tiles_w) % p.tiles_h;
-                const int tn = t / (p.tiles_w * p.tiles_h);
-                const int ow0 = tw * p.TW, oh0 = th * p.TH, n0 = tn * p.TN;
+        // TMA producer WARP: a stage is 4 + KW*(BN/32) boxes of [pix_tile x 32 channels] (MN-major operands cannot use wider
+        // boxes: one 128 B swizzle row = 32 fp32), up to 16 bulk-tensor instructions.  Issued by one thread they cost more than
+        // the stage's MMAs; here lane j issues box j, so a stage goes out in one pass.
+        int st = 0; uint32_t ph = 0;
+        const uint32_t tx = (uint32_t)stage_bytes;
+        const int nb_x = p.BN / 32;
+        const int n_boxes = 4 + p.KW * nb_x;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int tw = t % p.tiles_w;
+            const int th = (t / p.tiles_w) % p.tiles_h;
+            const int tn = t / (p.tiles_w * p.tiles_h);
+            const int ow0 = tw * p.TW, oh0 = th * p.TH, n0 = tn * p.TN;
+            if (lane == 0) {
                 mbar_wait(&empty_bar[st], ph ^ 1);
-                uint8_t* sa = smem + (size_t)st * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[st], tx);
-                for (int j = 0; j < 4; ++j)
-                    tma_load_4d(sa + j * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + j * 32, ow0, oh0, n0);
-                for (int kw = 0; kw < p.KW; ++kw)
-                    for (int j = 0; j < p.BN / 32; ++j)
-                        tma_load_4d(sa + a_bytes + kw * b1_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * 32,
-                                    ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
-                if (++st == p.stages) { st = 0; ph ^= 1; }
             }
+            __syncwarp();
+            uint8_t* sa = smem + (size_t)st * stage_bytes;
+            for (int b = lane; b < n_boxes; b += 32) {
+                if (b < 4) {
+                    tma_load_4d(sa + b * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + b * 32, ow0, oh0, n0);
+                } else {
+                    const int kw = (b - 4) / nb_x, j = (b - 4) - kw * nb_x;
+                    tma_load_4d(sa + a_bytes + kw * b1_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * 32,
+                                ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
+                }
+            }
+            __syncwarp();
+            if (++st == p.stages) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1 || warp == 6) {
         const int issuer = warp == 6 ? 1 : 0;
@@ -196,9 +206,11 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
     const int dual_env = tune(TK_WGRAD_DUAL);
     p.issuers = (KW >= 2 && dual_env) ? 2 : 1;
     const int units = KH * p.m_tiles * p.n_tiles;
-    int splits = (2 * num_sms() + units - 1) / units;
-    if (splits > p.pix_tiles) splits = p.pix_tiles;
+    // split-K so that units * splits fills whole waves of one CTA per SM: round DOWN (296 / 6 units = 49 -> 294 CTAs = 2 waves;
+    // rounding up gave 300 CTAs = a third wave with 4 CTAs)
+    int splits = (2 * num_sms()) / units;
     if (splits < 1) splits = 1;
+    if (splits > p.pix_tiles) splits = p.pix_tiles;
     p.splits = splits;
     const int stage_bytes = (4 + KW * (BN / 32)) * p.box_bytes;
     int stages = (200 * 1024) / stage_bytes;

@@ -20,7 +20,8 @@ Mapping onto the C ABI:
   * ConvTranspose2d k4 s2 p1 .................... mg_conv_igemm through ops.conv_dgrad (a transposed conv IS the data
                                                   gradient of the k4 s2 p1 conv with the same weight tensor)
   * 64 -> 3 7x7 head ............................ mg_conv_igemm with the 3 output channels padded to 32
-  * 4096-token attention ........................ torch.bmm / softmax (library GEMMs; 7 % of the net's FLOPs)
+  * 4096-token attention ........................ mg_conv_igemm (scores: Q x per-image K; output: P x per-image V^T) +
+                                                  mg_softmax_rows (probabilities written directly as the next operand)
 """
 import os
 
@@ -106,6 +107,15 @@ class InpaintGenerator(BaseNetwork):
         lo = (y32 - hi.float()).to(hi.dtype) if fmt == ops.BF16 else None
         return (fmt, hi, lo)
 
+    @staticmethod
+    def _conv_operand(operand, w, bias, cout, fmt):
+        """1x1 conv whose result is only needed as the operand of the next tensor-core product."""
+        wp = precision.pack_conv(w, None, operand[0])
+        if fmt == ops.TF32:
+            return (ops.TF32, precision.conv(operand, wp, cout, 1, 1, 1, 0, bias=bias, round_out=True), None)
+        _, hi, lo = precision.conv(operand, wp, cout, 1, 1, 1, 0, bias=bias, out16=(fmt, fmt == ops.BF16), want_f32=False)
+        return (fmt, hi, lo)
+
     def _conv(self, operand, w, inv_sigma, bias, cout, k, stride, pad):
         fmt = operand[0]
         return precision.conv(operand, precision.pack_conv(w, inv_sigma, fmt), cout, k, k, stride, pad, bias=bias)
@@ -164,11 +174,23 @@ class InpaintGenerator(BaseNetwork):
             att = mid[self.blocks]
             a = self._to_operand(h32, fmt)
             s, t = h32.shape[1], h32.shape[2]
-            q = self._conv(a, att.query_conv.weight.detach(), None, att.query_conv.bias.detach(), 64, 1, 1, 0).view(n, s * t, 64)
-            k = self._conv(a, att.key_conv.weight.detach(), None, att.key_conv.bias.detach(), 64, 1, 1, 0).view(n, s * t, 64)
-            v = self._conv(a, att.value_conv.weight.detach(), None, att.value_conv.bias.detach(), 256, 1, 1, 0).view(n, s * t, 256)
-            attn = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)
-            o = torch.bmm(attn, v).view(n, s, t, 256)
+            # softmax(Q K^T) V per image on the implicit-GEMM kernel: scores = 1x1 "conv" of Q with that image's K as the
+            # weight operand ([T keys] x [64]); probabilities = mg_softmax_rows, written in operand format; output = 1x1
+            # "conv" of the probabilities (T input channels) with V^T ([256] x [T]) as the weight operand.
+            T = s * t
+            qa = self._conv_operand(a, att.query_conv.weight.detach(), att.query_conv.bias.detach(), 64, fmt)
+            k = self._conv(a, att.key_conv.weight.detach(), None, att.key_conv.bias.detach(), 64, 1, 1, 0)            # [n,s,t,64]
+            v = self._conv(a, att.value_conv.weight.detach(), None, att.value_conv.bias.detach(), 256, 1, 1, 0)        # [n,s,t,256]
+            vt = ops.nhwc_to_nchw(v)                                                                                 # [n,256,s,t]
+            o = torch.empty((n, s, t, 256), device=x.device, dtype=torch.float32)
+            for i in range(n):
+                qi = (qa[0], qa[1][i:i + 1], qa[2][i:i + 1] if qa[2] is not None else None)
+                wk = precision.pack_conv(k[i].reshape(T, 64, 1, 1), None, fmt)
+                scores = precision.conv(qi, wk, T, 1, 1, 1, 0)                                                       # [1,s,t,T]
+                pfmt, phi, plo = ops.softmax_rows(scores.view(T, T), fmt, fmt == ops.BF16)
+                pa = (pfmt, phi.view(1, s, t, T), plo.view(1, s, t, T) if plo is not None else None)
+                wv = precision.pack_conv(vt[i].reshape(256, T, 1, 1), None, fmt)
+                ops.conv_igemm(pa[1], wv, 256, 1, 1, 1, 0, a_fmt=pfmt, x_lo=pa[2], out=o[i:i + 1])
             h32 = torch.cat([h32, o], dim=3).contiguous()
             # ---- decoder: two transposed convs (= data gradients of k4 s2 p1 convs), then the 7x7 head
             for idx, cout in ((0, 128), (3, 64)):

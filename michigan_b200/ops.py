@@ -332,6 +332,20 @@ def instance_norm_act(x, act=ACT_LRELU, eps=1e-5, round_out=False, pmul=None, ou
     return y
 
 
+def softmax_rows(x2d, fmt=TF32, split=False):
+    """Row softmax of a [rows, cols] fp32 matrix, emitted as a tensor-core operand: -> (fmt, hi_or_fp32, lo|None)."""
+    _chk(x2d, "scores")
+    rows, cols = x2d.shape
+    lib = _lib.load()
+    if fmt == TF32:
+        out = torch.empty_like(x2d)
+        check(lib.mg_softmax_rows(_p(x2d), rows, cols, _p(out), None, None, 0, 1, _stream()), "mg_softmax_rows")
+        return (TF32, out, None)
+    hi, lo = _alloc16((rows, cols), x2d.device, (fmt, split))
+    check(lib.mg_softmax_rows(_p(x2d), rows, cols, None, _p(hi), _p(lo), fmt, 0, _stream()), "mg_softmax_rows")
+    return (fmt, hi, lo)
+
+
 # ------------------------------------------------------------------------------------------ prep / pooling
 def prep_seg(tag_nchw, orient_nchw):
     _chk(tag_nchw, "input_tag"); _chk(orient_nchw, "orient")

@@ -276,18 +276,38 @@ def test_inpaint_forward_glue_with_torch_standins(monkeypatch):
         assert tuple(y.shape[2:]) == tuple(in_hw)
         return nhwc(y)
 
+    def softmax_rows(x2d, fmt=TF32, split=False):
+        pr = torch.softmax(x2d, dim=-1)
+        if fmt == TF32:
+            return (TF32, pr, None)
+        hi, lo = split16(pr, (fmt, split))
+        return (fmt, hi, lo)
+
+    def conv_igemm(hi, wpack, cout, kh, kw, stride=1, pad=0, *, a_fmt=TF32, x_lo=None, out=None, **kw_):
+        xx = hi.float() + (x_lo.float() if x_lo is not None else 0.0)
+        y = nhwc(F.conv2d(nchw(xx), wpack, None, stride=stride, padding=pad))
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
     fake_ops = SimpleNamespace(TF32=TF32, F16=F16, BF16=BF16, ACT_NONE=ACT_NONE, ACT_RELU=ACT_RELU, ACT_LRELU=ACT_LRELU,
                                nchw_to_nhwc=nchw_to_nhwc, pack_weight_thin=lambda w, cinp: w, conv_thin=conv_thin,
-                               instance_norm_act=instance_norm_act, reflect_pad=reflect_pad, conv_dgrad=conv_dgrad)
+                               instance_norm_act=instance_norm_act, reflect_pad=reflect_pad, conv_dgrad=conv_dgrad,
+                               nhwc_to_nchw=lambda t: nchw(t).contiguous(), softmax_rows=softmax_rows, conv_igemm=conv_igemm)
 
     def pack_conv(w, inv_sigma, fmt):
         return w * (inv_sigma if inv_sigma is not None else 1.0)
 
-    def conv(operand, wpack, cout, kh, kw, stride, pad, bias=None, **kw_):
+    def conv(operand, wpack, cout, kh, kw, stride, pad, bias=None, out16=None, want_f32=True, round_out=False, **kw_):
         fmt, hi, lo = operand
         x = hi.float() + (lo.float() if lo is not None else 0.0)
         assert wpack.shape[0] == cout and wpack.shape[2] == kh
-        return nhwc(F.conv2d(nchw(x), wpack, bias, stride=stride, padding=pad))
+        y = nhwc(F.conv2d(nchw(x), wpack, bias, stride=stride, padding=pad))
+        if out16 is not None:
+            h16, l16 = split16(y, out16)
+            return (y if want_f32 else None), h16, l16
+        return y
 
     for fmt_mode in (BF16, TF32):
         fake_prec = SimpleNamespace(conv_fmt=lambda c, m=fmt_mode: m, pack_conv=pack_conv, conv=conv)
