@@ -238,11 +238,16 @@ int mg_spectral_norm_batched(const void* descs, int n_layers, int max_O, int max
  * nn.Conv2d at the call sites listed for mg_conv_igemm). */
 int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                   int KH, int KW, int stride, int pad, void* stream);
+/* the same with bf16 operands (dy [N,OH,OW,Cout] and x [N,H,W,Cin] bf16; channels % 64 == 0), fp32 accumulation and output */
+int mg_conv_wgrad16(const void* dy16, const void* x16, float* dw_packed, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
+                    int stride, int pad, void* stream);
 
 /* Operand for the data gradient (transposed conv) of a conv with weight w [O,I,KH,KW]: sub-kernel
  * taps kh = k0h + stride*j (j < Jh), flipped and transposed to [I][Jh*Jw*O], times *inv_sigma, TF32. */
 int mg_pack_weight_dgrad(const float* w_oihw, float* out, int O, int I, int KH, int KW, int stride, int k0h, int Jh,
                          int k0w, int Jw, const float* inv_sigma, void* stream);
+/* fp32 -> 16-bit copy (fmt 1 = fp16, 2 = bf16, round to nearest): operands of the 16-bit gradient GEMMs. */
+int mg_cvt16(const float* src, void* dst, long long n, int fmt, void* stream);
 /* packed [O][KH*KW*I] weight gradient -> OIHW (accumulate != 0: +=). */
 int mg_unpack_wgrad(const float* dw_packed, float* dw_oihw, int O, int I, int KH, int KW, int accumulate, void* stream);
 
@@ -254,7 +259,10 @@ int mg_unpack_wgrad(const float* dw_packed, float* dw_oihw, int O, int I, int KH
  * order of the forward gamma|beta operand (TF32-rounded: operand of the two gradient GEMMs), dxhat
  * [N,H,W,C], and adds sum(dxhat), sum(dxhat*xhat) to sums [2*C] doubles (normalization.py:116 + BN). */
 int mg_spade_bwd(const float* dh, const float* h, const float* g1, const float* x, int x_shift, int N, int H, int W, int C,
-                 const float* nscale, const float* nshift, int act, int BN, float* dgb, float* dxhat, double* sums, void* stream);
+                 const float* nscale, const float* nshift, int act, int BN, float* dgb, float* dxhat, double* sums, void* dgb16,
+                 double* bias_sums, void* stream);
+/* (dgb16 != null: dgb is written as bf16 [N,H,W,2C] instead - the operand of the gamma|beta gradient GEMMs, its only consumers;
+ *  bias_sums != null: [2*C] doubles += per-channel sums of dgamma | dbeta = the mlp_gamma / mlp_beta bias gradients.) */
 /* dx[N,hs,ws,C] (+)= nscale * sum over the 2^x_shift x 2^x_shift children of (g - m1 - xhat*m2), m = sums/count
  * (batch-norm backward through a folded nearest upsample); count <= 0: read from sums[2*C] as in mg_bn_finalize;
  * sums == null: plain child sum (upsample backward). */

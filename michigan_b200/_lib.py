@@ -90,7 +90,9 @@ SIGNATURES = {
     "mg_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mg_conv_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_pad_channels32": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "mg_spade_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p],
+    "mg_spade_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p],
+    "mg_cvt16": [_p, _p, _ll, _i, _p],
+    "mg_conv_wgrad16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_bn_bwd_apply": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _d, _p, _i, _p],
     "mg_blend_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "mg_act_bwd": [_p, _p, _p, _ll, _i, _i, _p, _p, _i, _p],

@@ -7,6 +7,8 @@
 //   BN:  dx = ns*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat))   (means over the global N,h,w)
 //   IN:  same per (n,c) with g = dy*act'(xhat)
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdlib>
 #include <cmath>
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256)
 spade_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ hval, const float* __restrict__ g1,
                  const float* __restrict__ x, int xs, int N, int h, int w, int C, const float* __restrict__ ns,
                  const float* __restrict__ nh, int act, int BN, float* __restrict__ dgb, float* __restrict__ dxhat,
-                 double* __restrict__ sums, int blocks_total) {
+                 double* __restrict__ sums, int blocks_total, uint16_t* __restrict__ dgb16, double* __restrict__ bsums) {
     __shared__ float sh[256 * 8];
     const int G = C / 4;
     const int tpr = G < 256 ? G : 256;
@@ -73,6 +75,7 @@ spade_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ hval, c
     const int half = BN / 2;
     for (int g0 = tc; g0 < G; g0 += tpr) {
         float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        float sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};     // per-channel sums of dgamma, dbeta (the bias gradients)
         const int c0 = g0 * 4;
         float4 sc = make_float4(0, 0, 0, 0), sf = sc;
         if (threadIdx.x < rows * tpr) {
@@ -94,17 +97,28 @@ spade_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ hval, c
                 float dg[4], dxh[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    dg[i] = rtf32b(dp[i] * xh[i]);
+                    dg[i] = dp[i] * xh[i];
                     dxh[i] = dp[i] * gv[i];
                     a[i] += dxh[i];
                     b[i] = fmaf(dxh[i], xh[i], b[i]);
+                    sg[i] += dg[i];
+                    sb[i] += dp[i];
                 }
-                *reinterpret_cast<float4*>(dgb + p * 2 * C + col_g) = make_float4(dg[0], dg[1], dg[2], dg[3]);
-                *reinterpret_cast<float4*>(dgb + p * 2 * C + col_b) = make_float4(rtf32b(dp[0]), rtf32b(dp[1]), rtf32b(dp[2]), rtf32b(dp[3]));
+                if (dgb16) {
+                    // bf16 operand of the two gamma|beta gradient GEMMs (their only consumers)
+                    const __nv_bfloat162 g01 = __floats2bfloat162_rn(dg[0], dg[1]), g23 = __floats2bfloat162_rn(dg[2], dg[3]);
+                    const __nv_bfloat162 b01 = __floats2bfloat162_rn(dp[0], dp[1]), b23 = __floats2bfloat162_rn(dp[2], dp[3]);
+                    *reinterpret_cast<uint2*>(dgb16 + p * 2 * C + col_g) = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+                    *reinterpret_cast<uint2*>(dgb16 + p * 2 * C + col_b) = make_uint2(*reinterpret_cast<const uint32_t*>(&b01), *reinterpret_cast<const uint32_t*>(&b23));
+                } else {
+                    *reinterpret_cast<float4*>(dgb + p * 2 * C + col_g) = make_float4(rtf32b(dg[0]), rtf32b(dg[1]), rtf32b(dg[2]), rtf32b(dg[3]));
+                    *reinterpret_cast<float4*>(dgb + p * 2 * C + col_b) = make_float4(rtf32b(dp[0]), rtf32b(dp[1]), rtf32b(dp[2]), rtf32b(dp[3]));
+                }
                 *reinterpret_cast<float4*>(dxhat + p * C + c0) = make_float4(dxh[0], dxh[1], dxh[2], dxh[3]);
             }
         }
         reduce_rows_atomic(a, b, tpr, rows, tr, tc, g0, C, sums, sums + C, sh);
+        if (bsums) reduce_rows_atomic(sg, sb, tpr, rows, tr, tc, g0, C, bsums, bsums + C, sh);
     }
 }
 
@@ -865,10 +879,32 @@ __global__ void unpack_wgrad_gb_kernel(const float* __restrict__ dwp, float* __r
 using namespace mg;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+__global__ void cvt16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n4, int fmt) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        uint32_t lo, hi;
+        if (fmt == 1) {
+            const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+            lo = *reinterpret_cast<const uint32_t*>(&a); hi = *reinterpret_cast<const uint32_t*>(&b);
+        } else {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+            lo = *reinterpret_cast<const uint32_t*>(&a); hi = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2(lo, hi);
+    }
+}
+
+extern "C" int mg_cvt16(const float* src, void* dst, long long n, int fmt, void* stream) {
+    if (!src || !dst) return set_error(-1, "mg_cvt16: null pointer");
+    if (n % 4 != 0 || (fmt != 1 && fmt != 2)) return set_error(-2, "mg_cvt16: n %% 4 == 0, fmt 1 | 2");
+    cvt16_kernel<<<ew_grid_b(n / 4), 256, 0, ST(stream)>>>(src, static_cast<uint16_t*>(dst), n / 4, fmt);
+    return check_launch("mg_cvt16");
+}
+
 extern "C" int mg_spade_bwd(const float* dh, const float* h, const float* g1, const float* x, int x_shift, int N, int H, int W, int C,
                             const float* nscale, const float* nshift, int act, int BN, float* dgb, float* dxhat, double* sums,
-                            void* stream) {
-    if (!dh || !h || !g1 || !x || !nscale || !nshift || !dgb || !dxhat || !sums) return set_error(-1, "mg_spade_bwd: null pointer");
+                            void* dgb16, double* bias_sums, void* stream) {
+    if (!dh || !h || !g1 || !x || !nscale || !nshift || (!dgb && !dgb16) || !dxhat || !sums) return set_error(-1, "mg_spade_bwd: null pointer");
     if (C % 4 != 0 || C > 1024 || BN % 64 != 0 || (2 * C) % BN != 0) return set_error(-2, "mg_spade_bwd: bad C/BN");
     const int G = C / 4, tpr = G < 256 ? G : 256, rows = 256 / tpr;
     const long long P = (long long)N * H * W;
@@ -877,7 +913,7 @@ extern "C" int mg_spade_bwd(const float* dh, const float* h, const float* g1, co
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     spade_bwd_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(dh, h, g1, x, x_shift, N, H, W, C, nscale, nshift, act, BN, dgb, dxhat,
-                                                          sums, (int)blocks);
+                                                          sums, (int)blocks, static_cast<uint16_t*>(dgb16), bias_sums);
     return check_launch("mg_spade_bwd");
 }
 extern "C" int mg_bn_bwd_apply(const float* g, const float* x, int x_shift, int N, int hs, int ws, int C, const float* nscale,

@@ -29,7 +29,10 @@ struct WgradParams {
     int TW, TH, TN, tiles_w, tiles_h, tiles_n, pix_tiles;
     int BN, m_tiles, n_tiles, splits, stages;
     int issuers;               // 1 or 2 MMA-issuing threads (taps kw = j, j + issuers, ... belong to issuer j)
-    int pix_tile, box_bytes;   // K (pixels) per pipeline stage: 32 or 64; bytes of one [pix_tile x 32 ch] box
+    int pix_tile, box_bytes;   // K (pixels) per pipeline stage: 32 or 64; bytes of one [pix_tile x 128 B] box
+    int f16;                   // 0: fp32 storage read as TF32 (32 channels per 128 B row, K = 8 pixels per MMA);
+                               // 2: bf16 operands (64 channels per row, K = 16 pixels per MMA)
+    int kelem, mboxes, kmma;   // channels per box, boxes per 128-row M tile, pixels per MMA
     uint32_t idesc, tmem_cols;
     float* dw;  // [Cout][KH*KW*Cin]
 };
@@ -38,6 +41,18 @@ struct WgradParams {
 // TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 contiguous fp32 (128 B), 4 rows (K) per
 // 512 B swizzle atom.  LBO = byte distance between consecutive 32-element blocks along M/N,
 // SBO = distance between 4-row K groups (512 B for a dense box); one K=8 MMA spans two groups.
+// 16-bit MN-major operands use the plain 128B swizzle: rows of 64 contiguous elements (128 B), 8 rows (K) per 1024 B atom,
+// SBO = 1024 B between 8-row K groups (one K = 16 MMA spans two), LBO = distance between 64-element blocks along M/N.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_16(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -55,8 +70,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // One unit = one filter ROW (kh): the dY tile is loaded once per stage and multiplied with the KW shifted
     // input tiles (accumulators kw*BN.. in TMEM), so dY is streamed KH (not KH*KW) times from HBM/L2.
     const int kBoxBytes = p.box_bytes;
-    const int a_bytes = 4 * kBoxBytes;                 // M = 128 -> 4 boxes
-    const int b1_bytes = (p.BN / 32) * kBoxBytes;      // one tap's input tile
+    const int a_bytes = p.mboxes * kBoxBytes;           // M = 128 -> 4 boxes of 32 fp32 channels / 2 boxes of 64 bf16 channels
+    const int b1_bytes = (p.BN / p.kelem) * kBoxBytes;  // one tap's input tile
     const int stage_bytes = a_bytes + p.KW * b1_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full_bar = bars;
@@ -93,8 +108,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         // the stage's MMAs; here lane j issues box j, so a stage goes out in one pass.
         int st = 0; uint32_t ph = 0;
         const uint32_t tx = (uint32_t)stage_bytes;
-        const int nb_x = p.BN / 32;
-        const int n_boxes = 4 + p.KW * nb_x;
+        const int nb_x = p.BN / p.kelem;
+        const int n_boxes = p.mboxes + p.KW * nb_x;
         for (int t = t_begin; t < t_end; ++t) {
             const int tw = t % p.tiles_w;
             const int th = (t / p.tiles_w) % p.tiles_h;
@@ -107,11 +122,11 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             __syncwarp();
             uint8_t* sa = smem + (size_t)st * stage_bytes;
             for (int b = lane; b < n_boxes; b += 32) {
-                if (b < 4) {
-                    tma_load_4d(sa + b * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + b * 32, ow0, oh0, n0);
+                if (b < p.mboxes) {
+                    tma_load_4d(sa + b * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + b * p.kelem, ow0, oh0, n0);
                 } else {
-                    const int kw = (b - 4) / nb_x, j = (b - 4) - kw * nb_x;
-                    tma_load_4d(sa + a_bytes + kw * b1_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * 32,
+                    const int kw = (b - p.mboxes) / nb_x, j = (b - p.mboxes) - kw * nb_x;
+                    tma_load_4d(sa + a_bytes + kw * b1_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * p.kelem,
                                 ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
                 }
             }
@@ -128,10 +143,17 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                 for (int kw = issuer; kw < p.KW; kw += p.issuers)
-                    for (int k = 0; k < p.pix_tile / 8; ++k) {
-                        const uint64_t da = umma_desc_mnmajor_sw128(sa + k * 1024, kBoxBytes);
-                        const uint64_t db = umma_desc_mnmajor_sw128(sa + a_bytes + kw * b1_bytes + k * 1024, kBoxBytes);
-                        umma_tf32(tmem_base + (uint32_t)(kw * p.BN), da, db, p.idesc, (first && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < p.pix_tile / p.kmma; ++k) {
+                        const uint32_t koff = (uint32_t)(k * p.kmma * 128);      // kmma pixel rows of 128 B
+                        if (p.f16) {
+                            const uint64_t da = umma_desc_mnmajor_sw128_16(sa + koff, kBoxBytes);
+                            const uint64_t db = umma_desc_mnmajor_sw128_16(sa + a_bytes + kw * b1_bytes + koff, kBoxBytes);
+                            umma_f16(tmem_base + (uint32_t)(kw * p.BN), da, db, p.idesc, (first && k == 0) ? 0u : 1u);
+                        } else {
+                            const uint64_t da = umma_desc_mnmajor_sw128(sa + koff, kBoxBytes);
+                            const uint64_t db = umma_desc_mnmajor_sw128(sa + a_bytes + kw * b1_bytes + koff, kBoxBytes);
+                            umma_tf32(tmem_base + (uint32_t)(kw * p.BN), da, db, p.idesc, (first && k == 0) ? 0u : 1u);
+                        }
                     }
                 first = 0;
                 umma_commit(&empty_bar[st]);
@@ -178,22 +200,25 @@ static int np2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 using namespace mg;
 
 // dw: [Cout][KH*KW*Cin] fp32 (tap-major K, the layout of mg_pack_weight); zeroed here when split-K > 1.
-extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
-                             int KH, int KW, int stride, int pad, void* stream_) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// fmt 0: dy / x fp32 (read as TF32); fmt 2: dy / x bf16.
+static int wgrad_launch(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                        int KH, int KW, int stride, int pad, int fmt, cudaStream_t stream) {
     if (!dy || !x || !dw) return set_error(-1, "mg_conv_wgrad: null pointer");
-    if (Cin % 32 != 0 || Cout % 32 != 0) return set_error(-2, "mg_conv_wgrad: channels must be multiples of 32");
+    if (fmt != 0 && fmt != 2) return set_error(-5, "mg_conv_wgrad: operand format must be 0 (tf32) or 2 (bf16)");
+    const int kelem = fmt ? 64 : 32;
+    if (Cin % kelem != 0 || Cout % kelem != 0) return set_error(-2, "mg_conv_wgrad: channels must be multiples of %d", kelem);
     WgradParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout; p.Cin = Cin; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+    p.f16 = fmt; p.kelem = kelem; p.mboxes = 128 / kelem; p.kmma = fmt ? 16 : 8;
     int BN = Cin >= 128 ? 128 : Cin;
-    if (Cin % BN != 0) BN = 32;
+    if (Cin % BN != 0) BN = kelem;
     while (KW * BN > 512) BN /= 2;                       // KW accumulators of BN columns must fit TMEM
-    if (BN < 32 || Cin % BN != 0) return set_error(-3, "mg_conv_wgrad: KW %d x Cin %d does not fit TMEM", KW, Cin);
+    if (BN < kelem || Cin % BN != 0) return set_error(-3, "mg_conv_wgrad: KW %d x Cin %d does not fit TMEM", KW, Cin);
     p.BN = BN;
     // K (pixels) per stage: 64 when at least 3 stages fit in shared memory, else 32
     int pix_tile = 64;
-    if ((200 * 1024) / ((4 + KW * (BN / 32)) * 64 * 128) < 3) pix_tile = 32;
+    if ((200 * 1024) / ((p.mboxes + KW * (BN / kelem)) * 64 * 128) < 3) pix_tile = 32;
     p.pix_tile = pix_tile; p.box_bytes = pix_tile * 128;
     p.TW = np2(OW) < 8 ? np2(OW) : 8;
     int th = pix_tile / p.TW;
@@ -212,31 +237,34 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
     if (splits < 1) splits = 1;
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     p.splits = splits;
-    const int stage_bytes = (4 + KW * (BN / 32)) * p.box_bytes;
+    const int stage_bytes = (p.mboxes + KW * (BN / kelem)) * p.box_bytes;
     int stages = (200 * 1024) / stage_bytes;
     if (stages < 1) return set_error(-4, "mg_conv_wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
     if (stages > kWgStagesMax) stages = kWgStagesMax;
     p.stages = stages;
-    // TF32 x TF32 -> F32, A and B both MN-major (bits 15, 16), M = 128, N = BN
-    p.idesc = umma_idesc_tf32(128, BN) | (1u << 15) | (1u << 16);
+    // A and B both MN-major (bits 15, 16), M = 128, N = BN, fp32 accumulate
+    p.idesc = (fmt ? umma_idesc_16(128, BN, 2) : umma_idesc_tf32(128, BN)) | (1u << 15) | (1u << 16);
     int tc = np2(KW * BN); p.tmem_cols = tc < 32 ? 32 : tc;
     p.dw = dw;
 
     CUtensorMap tmDY, tmX;
+    const int esz = fmt ? 2 : 4;
+    const CUtensorMapDataType dt = fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = fmt ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        cuuint64_t strides[3] = {(cuuint64_t)Cout * esz, (cuuint64_t)OW * Cout * esz, (cuuint64_t)OH * OW * Cout * esz};
+        cuuint32_t box[4] = {(cuuint32_t)kelem, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, 1, 1, 1};
-        int rc = encode_tensor_map(&tmDY, (void*)dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = encode_tensor_map(&tmDY, (void*)dy, dt, 4, dims, strides, box, es, sw);
         if (rc) return rc;
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * esz, (cuuint64_t)W * Cin * esz, (cuuint64_t)H * W * Cin * esz};
+        cuuint32_t box[4] = {(cuuint32_t)kelem, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        int rc = encode_tensor_map(&tmX, (void*)x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = encode_tensor_map(&tmX, (void*)x, dt, 4, dims, strides, box, es, sw);
         if (rc) return rc;
     }
     if (splits > 1) {
@@ -253,4 +281,15 @@ extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, 
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
     wgrad_tf32_kernel<<<units * splits, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, p);
     return check_launch("mg_conv_wgrad");
+}
+
+extern "C" int mg_conv_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                             int KH, int KW, int stride, int pad, void* stream_) {
+    return wgrad_launch(dy, x, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, 0, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// Same with 16-bit (bf16) operands: dy [N,OH,OW,Cout] and x [N,H,W,Cin] bf16, fp32 accumulation and output.
+extern "C" int mg_conv_wgrad16(const void* dy16, const void* x16, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                               int KH, int KW, int stride, int pad, void* stream_) {
+    return wgrad_launch(dy16, x16, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, 2, reinterpret_cast<cudaStream_t>(stream_));
 }

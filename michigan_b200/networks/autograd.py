@@ -15,7 +15,7 @@ from types import SimpleNamespace
 
 import torch
 
-from .. import ops
+from .. import ops, precision
 from .sync_batchnorm import allreduce_sums
 
 _RELU, _LRELU, _NONE = ops.ACT_RELU, ops.ACT_LRELU, ops.ACT_NONE
@@ -51,15 +51,6 @@ def _thin_wt_to_oihw(dwt, kh, kw, cin):
     return dwt.view(kh, kw, cp, co).permute(3, 2, 0, 1)[:, :cin].contiguous()
 
 
-def _gb_unpack_index(c, device):
-    """packed gamma|beta row order -> (gamma idx, beta idx) into the [2C] packed vector."""
-    bn = ops.spade_bn(c)
-    half = bn // 2
-    ch = torch.arange(c, device=device)
-    tile, r = ch // half, ch % half
-    return tile * bn + r, tile * bn + half + r
-
-
 # =============================================================================================== conv helpers
 def _conv_weight(conv, inv_of):
     """(w_oihw source, inv_sigma or None, is_sn)."""
@@ -86,19 +77,27 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad)
     w, isg, _ = _conv_weight(conv, inv_of)
     dh = ops.conv_dgrad(dy, w.detach(), S.hw, 1, pad, inv_sigma=isg)
-    dgb, dxhat, sums = ops.spade_bwd(dh, S.h, S.g1, S.src, S.shift, S.ns, S.nh, S.act)
+    gfmt = precision.grad_fmt()
+    dgb, dxhat, sums, bsum = ops.spade_bwd(dh, S.h, S.g1, S.src, S.shift, S.ns, S.nh, S.act, dgb_fmt=gfmt)
     del dh
     sp = S.sp
     c = S.src.shape[-1]
-    actv = ops.mlp_shared(seg4, S.wsh, sp.mlp_shared[0].bias.detach(), seg_resize=S.R, act=_RELU, round_out=True, out_hw=S.hw)
-    dwg, dwb = ops.unpack_wgrad_gb(ops.conv_wgrad(dgb, actv, 3, 3, 1, 1), c, 128)
+    wdg = ops.pack_weight_dgrad_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach())
+    if gfmt == ops.TF32:
+        actv = ops.mlp_shared(seg4, S.wsh, sp.mlp_shared[0].bias.detach(), seg_resize=S.R, act=_RELU, round_out=True, out_hw=S.hw)
+        dwp = ops.conv_wgrad(dgb, actv, 3, 3, 1, 1)
+        dactv = ops.conv_igemm(dgb, wdg, 128, 3, 3, 1, 1)
+    else:
+        actv, actv16, _ = ops.mlp_shared(seg4, S.wsh, sp.mlp_shared[0].bias.detach(), seg_resize=S.R, act=_RELU, out_hw=S.hw,
+                                         out16=(gfmt, False))
+        dwp = ops.conv_wgrad16(dgb, actv16, 3, 3, 1, 1)
+        del actv16
+        dactv = ops.conv_igemm(dgb, ops.cvt16(wdg, gfmt), 128, 3, 3, 1, 1, a_fmt=gfmt)
+    dwg, dwb = ops.unpack_wgrad_gb(dwp, c, 128)
     G.add(sp.mlp_gamma.weight, dwg)
     G.add(sp.mlp_beta.weight, dwb)
-    gi, bi = _gb_unpack_index(c, dgb.device)
-    bsum = ops.chan_sum(dgb)
-    G.add(sp.mlp_gamma.bias, bsum[gi])
-    G.add(sp.mlp_beta.bias, bsum[bi])
-    dactv = ops.conv_igemm(dgb, ops.pack_weight_dgrad_gb(sp.mlp_gamma.weight.detach(), sp.mlp_beta.weight.detach()), 128, 3, 3, 1, 1)
+    G.add(sp.mlp_gamma.bias, bsum[:c].float())
+    G.add(sp.mlp_beta.bias, bsum[c:].float())
     del dgb
     da = ops.act_bwd(dactv, actv, _RELU)
     del dactv, actv

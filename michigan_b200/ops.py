@@ -517,17 +517,40 @@ def chan_sum(x):
     return bn_sums(x)[: x.shape[-1]].float()
 
 
-def spade_bwd(dh, h, g1, x, x_shift, nscale, nshift, act):
-    """-> (dgb [N,H,W,2C] packed gamma|beta grads, dxhat [N,H,W,C], sums [2C] float64)."""
+def spade_bwd(dh, h, g1, x, x_shift, nscale, nshift, act, dgb_fmt=TF32):
+    """-> (dgb [N,H,W,2C] packed gamma|beta grads (fp32 TF32-rounded, or bf16 when dgb_fmt=BF16: the operand of the two
+    gamma|beta gradient GEMMs), dxhat [N,H,W,C], sums [2C+1] float64, bias_sums [2C] float64 = per-channel sums of dgamma | dbeta)."""
     for t, nm in ((dh, "dh"), (h, "h"), (g1, "g1"), (x, "x")):
         _chk(t, nm)
     N, H, W, Cc = dh.shape
-    dgb = torch.empty((N, H, W, 2 * Cc), device=dh.device, dtype=torch.float32)
+    dgb = torch.empty((N, H, W, 2 * Cc), device=dh.device, dtype=_dt(dgb_fmt))
     dxhat = torch.empty_like(dh)
     sums = torch.zeros(2 * Cc + 1, device=dh.device, dtype=torch.float64)   # + the sample-count slot (see bn_sums)
+    bsums = torch.zeros(2 * Cc, device=dh.device, dtype=torch.float64)
+    is16 = dgb_fmt != TF32
     check(_lib.load().mg_spade_bwd(_p(dh), _p(h), _p(g1), _p(x), x_shift, N, H, W, Cc, _p(nscale), _p(nshift), act, spade_bn(Cc),
-                                   _p(dgb), _p(dxhat), _p(sums), _stream()), "mg_spade_bwd")
-    return dgb, dxhat, sums
+                                   None if is16 else _p(dgb), _p(dxhat), _p(sums), _p(dgb) if is16 else None, _p(bsums), _stream()),
+          "mg_spade_bwd")
+    return dgb, dxhat, sums, bsums
+
+
+def cvt16(x, fmt=BF16):
+    """fp32 -> 16-bit copy (round to nearest) on the current stream."""
+    _chk(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=_T16[fmt])
+    check(_lib.load().mg_cvt16(_p(x), _p(out), x.numel(), fmt, _stream()), "mg_cvt16")
+    return out
+
+
+def conv_wgrad16(dy16, x16, kh, kw, stride=1, pad=0):
+    """conv_wgrad with bf16 operands (fp32 accumulation and result)."""
+    _chk(dy16, "dy16", torch.bfloat16); _chk(x16, "x16", torch.bfloat16)
+    N, H, W, Cin = x16.shape
+    _, OH, OW, Cout = dy16.shape
+    dw = torch.empty((Cout, kh * kw * Cin), device=x16.device, dtype=torch.float32)
+    check(_lib.load().mg_conv_wgrad16(_p(dy16), _p(x16), _p(dw), N, H, W, Cin, OH, OW, Cout, kh, kw, stride, pad, _stream()),
+          "mg_conv_wgrad16")
+    return dw
 
 
 def bn_bwd_apply(g, x, x_shift, nscale, nshift, sums, count, dx=None):

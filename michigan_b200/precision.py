@@ -36,14 +36,24 @@ def gb_fmt(cin=128):
     return ops.F16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
 
 
-def gb_policy(h):
-    """(fmt, split) of the SPADE gamma/beta GEMM at feature height h.  The low-resolution blocks
-    (head_0, G_middle_0/1, up_0: h <= 64, 6 % of the gamma/beta FLOPs) feed every later batch-norm, so
-    their GEMMs use the three-pass bf16 split; emulation on the 512x512 net: image max-abs error
-    1.0e-3 -> 4.9e-4."""
+def gb_policy(ratio):
+    """(fmt, split) of the SPADE gamma/beta GEMM of a block whose feature map is 1/`ratio` of the segmap resolution.  The
+    low-resolution blocks (head_0, G_middle_0/1, up_0: ratio >= 8, 6 % of the gamma/beta FLOPs) feed every later batch-norm, so
+    their GEMMs use the three-pass bf16 split; emulation on the 512x512 net: image max-abs error 1.0e-3 -> 4.9e-4.
+    The criterion is the block's DEPTH (resolution ratio), not its absolute height: with --add_feat_zeros the same blocks run at
+    9..72 instead of 8..64 pixels (measured: keying on h <= 64 left up_0 in one-pass fp16 at 576x576 and the image error at
+    2.5e-3)."""
     if _mode != "mixed16":
         return ops.TF32, False
-    return (ops.BF16, True) if h <= 64 else (ops.F16, False)
+    return (ops.BF16, True) if ratio >= 8 else (ops.F16, False)
+
+
+def grad_fmt():
+    """Operand format of the SPADE gamma|beta GRADIENT GEMMs (data gradient w.r.t. actv and weight gradient: 2/3 of the backward
+    FLOPs): bf16 operands, fp32 accumulation.  They only feed the mlp_shared / mlp_gamma / mlp_beta parameter gradients, i.e. sums
+    over 10^5..10^6 pixels in which bf16's 2^-9 operand rounding averages out (measured gradient cosine vs the fp32 reference in
+    tests/test_gpu_parity.py); dgamma|dbeta is produced directly in bf16 by mg_spade_bwd.  TF32 in "tf32" mode."""
+    return ops.BF16 if _mode == "mixed16" else ops.TF32
 
 
 def conv_fmt(cin):

@@ -218,6 +218,22 @@ def test_tensor_core_wgrad_and_dgrad(gen, N, h, Cin, Cout, k, s, p):
     assert rel_err(nchw(dx), x.grad) <= 5e-5
 
 
+@pytest.mark.parametrize("N,h,Cin,Cout,k,s,p", [(2, 32, 64, 64, 3, 1, 1), (2, 40, 128, 256, 3, 1, 1), (2, 33, 64, 128, 4, 2, 2), (3, 8, 128, 64, 1, 1, 0)])
+def test_wgrad_bf16_operands(gen, N, h, Cin, Cout, k, s, p):
+    """The weight-gradient GEMM with bf16 operands (MN-major, plain 128B swizzle, K = 16 pixels per MMA) against torch autograd on
+    bf16-exact operands (fp32 accumulation on both sides)."""
+    ops = _ops()
+    x = torch.randn(N, Cin, h, h, generator=gen).to(dev).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).to(dev).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride=s, padding=p)
+    dy = torch.randn(y.shape, generator=gen).to(dev).bfloat16().float()
+    y.backward(dy)
+    dwp = ops.conv_wgrad16(nhwc(dy).bfloat16(), nhwc(x.detach()).bfloat16(), k, k, s, p)
+    dw = ops.unpack_wgrad(dwp, tuple(w.shape))
+    assert rel_err(dw, w.grad) <= 5e-5
+    assert torch.equal(ops.cvt16(nhwc(dy)), nhwc(dy).bfloat16())
+
+
 @pytest.mark.parametrize("fmt", ["tf32", "f16", "bf3"])
 def test_igemm_dual_pipelines_n256(gen, fmt):
     """Same as test_igemm_dual_pipelines for a 256-column accumulator (ring of 2 + 2 stages), MG_DUAL=2 (the default schedule)."""

@@ -455,7 +455,7 @@ def group_bwd2():
         hh.backward(dh)
         ns = rstd.view(-1).detach().contiguous()
         nh = (-mean.view(-1) * rstd.view(-1)).detach().contiguous()
-        dgb, dxhat, sums = ops.spade_bwd(nhwc(dh), nhwc(hh.detach()), nhwc((1 + gamma).detach()), nhwc(x.detach()), xs, ns, nh, act)
+        dgb, dxhat, sums, _bs = ops.spade_bwd(nhwc(dh), nhwc(hh.detach()), nhwc((1 + gamma).detach()), nhwc(x.detach()), xs, ns, nh, act)
         dx = ops.bn_bwd_apply(dxhat, nhwc(x.detach()), xs, ns, nh, sums, N * h * h)
         torch.cuda.synchronize()
         bn = ops.spade_bn(C); half = bn // 2
