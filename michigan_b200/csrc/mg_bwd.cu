@@ -550,9 +550,12 @@ conv_img_wgrad_kernel(const float* __restrict__ dz4, const float* __restrict__ x
     float* dz_s = sm + (size_t)NP * (Cin + 1);   // [256][4]
     // thread -> (ci, tap group): Cin*9 products per co; threads = 256: each handles (ci = t % Cin, taps t/Cin .. step 256/Cin)
     const int ci = threadIdx.x % Cin, tg = threadIdx.x / Cin, tgn = 256 / Cin;
-    float acc[9][3];
+    // taps of this thread: tg, tg + tgn, tg + 2*tgn, ... (at most 5 for Cin <= 128); the accumulators are indexed by the UNROLLED
+    // slot j, never by the run-time tap (a run-time index put the whole array in local memory: 2.5 ms per call)
+    constexpr int kSlots = 5;
+    float acc[kSlots][3];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.f;
+    for (int j = 0; j < kSlots; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
     float bacc[3] = {0, 0, 0};
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
@@ -589,10 +592,14 @@ conv_img_wgrad_kernel(const float* __restrict__ dz4, const float* __restrict__ x
             for (int pp = 0; pp < 256; ++pp) {
                 const float4 d = *reinterpret_cast<const float4*>(dz_s + pp * 4);
                 const int ly = pp >> 5, lx = pp & 31;
-                for (int t = tg; t < 9; t += tgn) {
-                    const int kh = t / 3, kw = t - kh * 3;
-                    const float v = in_s[(size_t)((ly + kh) * PW + lx + kw) * (Cin + 1) + ci];
-                    acc[t][0] = fmaf(d.x, v, acc[t][0]); acc[t][1] = fmaf(d.y, v, acc[t][1]); acc[t][2] = fmaf(d.z, v, acc[t][2]);
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) {
+                    const int t = tg + j * tgn;
+                    if (t < 9) {
+                        const int kh = t / 3, kw = t - kh * 3;
+                        const float v = in_s[(size_t)((ly + kh) * PW + lx + kw) * (Cin + 1) + ci];
+                        acc[j][0] = fmaf(d.x, v, acc[j][0]); acc[j][1] = fmaf(d.y, v, acc[j][1]); acc[j][2] = fmaf(d.z, v, acc[j][2]);
+                    }
                 }
             }
         }
@@ -608,9 +615,17 @@ conv_img_wgrad_kernel(const float* __restrict__ dz4, const float* __restrict__ x
             if (threadIdx.x == 2) bacc[2] += s2;
         }
     }
-    if (tg < tgn)
-        for (int t = tg; t < 9; t += tgn)
-            for (int co = 0; co < Cout; ++co) atomicAdd(dw + ((size_t)co * Cin + ci) * 9 + t, acc[t][co]);
+    if (tg < tgn) {
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+            const int t = tg + j * tgn;
+            if (t < 9) {
+#pragma unroll
+                for (int co = 0; co < 3; ++co)
+                    if (co < Cout) atomicAdd(dw + ((size_t)co * Cin + ci) * 9 + t, acc[j][co]);
+            }
+        }
+    }
     if (threadIdx.x < Cout && db) atomicAdd(db + threadIdx.x, bacc[threadIdx.x]);
 }
 
@@ -1038,7 +1053,7 @@ extern "C" int mg_conv_to1_bwd(const float* dl, const float* x, const float* w, 
         count_launch();
     }
     if (dw) {
-        dim3 grid(num_sms(), KH * KW);
+        dim3 grid(num_sms() * 4, KH * KW);      // latency-bound per-thread pixel loops: 4x the blocks (was 0.5 ms per call)
         conv_to1_wgrad_kernel<<<grid, 128, 0, ST(stream)>>>(dl, x, dw, db, N, H, W, Cin, KH, KW, pad, OH, OW);
     }
     return check_launch("mg_conv_to1_bwd");
