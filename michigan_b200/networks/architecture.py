@@ -122,6 +122,8 @@ class SPADEResnetBlock(nn.Module):
                 operand = (cfmt, hi, lo)
             S = SimpleNamespace(sp=getattr(self, name), src=src, shift=shift, ns=nscale, nh=nshift, act=act, g1=g1, h=h32,
                                 wsh=wsh, R=R, hw=(h, w))
+            if cfmt == ops.BF16 and precision.conv_grad_fmt() == ops.BF16:
+                S.h16 = operand[1]          # the forward's bf16 hi operand doubles as the weight-gradient GEMM's input
             return operand, S
 
         if save is not None:

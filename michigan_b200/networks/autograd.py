@@ -59,10 +59,24 @@ def _conv_weight(conv, inv_of):
     return conv.weight, None, False
 
 
-def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_bias=True, dz_for_bias=None):
-    """Weight (+bias) gradients of an implicit-GEMM conv; dy: [N,OH,OW,Cout], a_operand: its fp32 input."""
+def _grad16(t):
+    """bf16 copy of a gradient / activation tensor when the conv gradient GEMMs run in bf16 and its channels allow it."""
+    if precision.conv_grad_fmt() == ops.BF16 and t.shape[-1] % 64 == 0:
+        return ops.cvt16(t, ops.BF16)
+    return None
+
+
+def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_bias=True, dz_for_bias=None, dy16=None, a16=None):
+    """Weight (+bias) gradients of an implicit-GEMM conv; dy: [N,OH,OW,Cout], a_operand: its fp32 input.
+    dy16 / a16: bf16 copies (both given -> bf16 weight-gradient GEMM)."""
     w, isg, is_sn = _conv_weight(conv, inv_of)
-    dwt = ops.unpack_wgrad(ops.conv_wgrad(dy, a_operand, kh, kw, stride, pad), tuple(w.shape))
+    if dy16 is not None and a16 is None and a_operand.shape[-1] % 64 == 0:
+        a16 = ops.cvt16(a_operand, ops.BF16)
+    if dy16 is not None and a16 is not None:
+        dwp = ops.conv_wgrad16(dy16, a16, kh, kw, stride, pad)
+    else:
+        dwp = ops.conv_wgrad(dy, a_operand, kh, kw, stride, pad)
+    dwt = ops.unpack_wgrad(dwp, tuple(w.shape))
     if is_sn:
         G.add(w, ops.spectral_norm_bwd(dwt, w.detach(), conv.weight_u, conv.weight_v, isg))
     else:
@@ -74,9 +88,11 @@ def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_
 # =============================================================================================== SPADE + conv
 def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     """Backward of conv(act(SPADE(src))) given dy; returns (dxhat, sums) for the BN backward of `src`."""
-    _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad)
+    dy16 = _grad16(dy)
+    _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad, dy16=dy16, a16=getattr(S, "h16", None))
     w, isg, _ = _conv_weight(conv, inv_of)
-    dh = ops.conv_dgrad(dy, w.detach(), S.hw, 1, pad, inv_sigma=isg)
+    dh = ops.conv_dgrad(dy, w.detach(), S.hw, 1, pad, inv_sigma=isg, dy16=dy16)
+    del dy16
     gfmt = precision.grad_fmt()
     dgb, dxhat, sums, bsum = ops.spade_bwd(dh, S.h, S.g1, S.src, S.shift, S.ns, S.nh, S.act, dgb_fmt=gfmt)
     del dh

@@ -471,10 +471,13 @@ def dgrad_geometry(k, stride, pad, r):
     return k0, J, J - 1 - d0
 
 
-def conv_dgrad(dy, w_oihw, in_hw, stride=1, pad=0, inv_sigma=None, out=None, accumulate=False):
+def conv_dgrad(dy, w_oihw, in_hw, stride=1, pad=0, inv_sigma=None, out=None, accumulate=False, dy16=None):
     """dX [N,H,W,Cin] of y = conv(x, w, stride, pad) given dY [N,OH,OW,Cout]; tcgen05 implicit GEMM on dY
-    with flipped/transposed (sub-)kernels, one launch per output parity class (stride^2)."""
-    _chk(dy, "dy"); _chk(w_oihw, "w")
+    with flipped/transposed (sub-)kernels, one launch per output parity class (stride^2).
+    dy16: bf16 copy of dY -> the GEMM runs with bf16 operands (weights converted after packing), fp32 accumulation."""
+    _chk(dy, "dy"); _chk(w_oihw, "w"); _chk(dy16, "dy16", torch.bfloat16)
+    if dy16 is not None and (dy.shape[-1] % 64 != 0):
+        dy16 = None
     N, OH, OW, Cout = dy.shape
     O, I, KH, KW = w_oihw.shape
     H, W = in_hw
@@ -499,7 +502,10 @@ def conv_dgrad(dy, w_oihw, in_hw, stride=1, pad=0, inv_sigma=None, out=None, acc
                   "mg_pack_weight_dgrad")
             extra = dict(pad_h_extra=ph, pad_w_extra=pw, out_stride=stride, out_off_h=rh, out_off_w=rw, OHF=H, OWF=W,
                          accumulate=int(accumulate))
-            conv_igemm(dy, wp, I, Jh, Jw, 1, 0, out=out, out_hw=(ah, aw), _extra=extra)
+            if dy16 is not None:
+                conv_igemm(dy16, cvt16(wp, BF16), I, Jh, Jw, 1, 0, out=out, out_hw=(ah, aw), _extra=extra, a_fmt=BF16)
+            else:
+                conv_igemm(dy, wp, I, Jh, Jw, 1, 0, out=out, out_hw=(ah, aw), _extra=extra)
     return out
 
 

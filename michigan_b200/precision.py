@@ -56,6 +56,14 @@ def grad_fmt():
     return ops.BF16 if _mode == "mixed16" else ops.TF32
 
 
+def conv_grad_fmt():
+    """Operand format of the OTHER gradient GEMMs (conv_0 / conv_1 / conv_s, encoders, discriminator: data and weight
+    gradients).  TF32 by default; MICHIGAN_B200_GRAD16=all runs them with bf16 operands too (dY converted once per layer, the
+    forward's bf16 hi operand reused as the weight-gradient input) - an experiment, see DESIGN.md §5."""
+    import os
+    return ops.BF16 if (_mode == "mixed16" and os.environ.get("MICHIGAN_B200_GRAD16", "") == "all") else ops.TF32
+
+
 def conv_fmt(cin):
     """Operand format of the split-precision convs (BF16 -> three passes) or TF32 (one pass)."""
     return ops.BF16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
