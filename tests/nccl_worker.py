@@ -109,13 +109,14 @@ def main():
             stat_err = max(stat_err, (got[n].cpu() - v.detach()).abs().max().item() / max(1.0, v.abs().max().item()))
     res["running_stats_uv_rel_err_vs_oracle"] = stat_err
     res["buffers_bit_identical"] = all(_bits_equal_across_ranks(b) for b in model.netG.buffers())
+    res["buffers_differing"] = [n for n, b in model.netG.named_buffers() if not _bits_equal_across_ranks(b)][:6]
     named = dict(model.netG.named_parameters())
     res["grads_bit_identical"] = all(_bits_equal_across_ranks(p_.grad) for p_ in model.netG.parameters() if p_.grad is not None)
     worst_cos, worst_rel = 1.0, 0.0
     gmax = max(osdG[n].grad.norm().item() for n in namesG if osdG[n].grad is not None)
     for n in namesG:
         r = osdG[n].grad
-        if r is None or n.endswith("conv_0.bias") or n.endswith("conv_1.bias") and False:
+        if r is None:
             continue
         gq = named[n].grad
         if gq is None:

@@ -212,9 +212,14 @@ def test_generator_add_feat_zeros_576_eval_vs_oracle():
     sd = reference_layout_state("G", dict(cfg, size=512), 24)
     # Running statistics of a trained checkpoint describe the data it is used on; fill_state_dict leaves mean 0 / var 1,
     # and statistics from a different geometry make |x_hat| large (eval-mode BN does not re-normalise), which amplifies the
-    # operand rounding of the gamma/beta GEMMs beyond anything a real checkpoint sees.  So: one train-mode oracle pass over
-    # the SAME zero-padded 576x576 geometry (different noise/image seed) with momentum 1 writes its batch statistics into sd.
-    _, pre_cal = preprocessed(dict(cfg, data_seed=14))
+    # operand rounding of the gamma/beta GEMMs beyond anything a real checkpoint sees (measured: statistics of ONE other image -
+    # 81 samples per channel in head_0 - leave a 2e-3 tail while the mean error stays at 1.4e-5).  So: one train-mode oracle
+    # pass over FOUR other images of the same zero-padded 576x576 geometry, momentum 1, writes its batch statistics into sd.
+    _, pre_cal = preprocessed(dict(cfg, data_seed=14, batch=4))
+    g = torch.Generator().manual_seed(77)
+    pre_cal["image_ref"] = torch.rand(4, 3, 512, 512, generator=g) * 2 - 1
+    pre_cal["image_tag"] = pre_cal["image_ref"].clone()
+    pre_cal["noise"] = torch.rand(4, 3, 512, 512, generator=g)
     with torch.no_grad():
         orc.generate_fake(sd, orc.default_opt(isTrain=True, add_feat_zeros=True), pre_cal, True, rng_k=5, momentum=1.0)
     assert float(sd["up_3.norm_0.param_free_norm.running_var"].mean()) != 1.0
