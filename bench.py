@@ -224,8 +224,8 @@ def run_reference_arm(a):
 # DRAM traffic of one launch of the dominant kernel from the `ncu --set full` capture committed under profiles/
 # (dram__bytes_read.sum + dram__bytes_write.sum at N=8); algorithmic bytes = actv fp16 268 MB + x fp32 268 MB + weights
 # 0.6 MB read, bf16 hi+lo 537 MB written.
-NCU_TRAFFIC_BYTES_N8 = 817.437696e6 + 1028.886e6
-NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_spade_gemm_f16_final.txt"
+NCU_TRAFFIC_BYTES_N8 = 810.322432e6 + 1027.503e6
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_spade_gemm_f16.txt"
 
 
 def _time_kernel(f, reps=5):
@@ -296,17 +296,24 @@ def worst_kernel_roofline(batch):
 
 
 def wgrad_kernel_roofline(batch):
-    """Dominant kernel of the train step (27 % of it): the weight-gradient GEMM, at the shape of the SPADE
-    gamma|beta wgrad of up_3 (dY = dgamma|dbeta [N,512,512,256], X = actv [N,512,512,128], 3x3): 2 * N*512*512 * 1152 * 256
-    FLOPs per launch, TF32 operands."""
-    from michigan_b200 import ops
+    """Dominant kernel of the train step: the weight-gradient GEMM, at the shape of the SPADE gamma|beta wgrad of up_3
+    (dY = dgamma|dbeta [N,512,512,256], X = actv [N,512,512,128], 3x3): 2 * N*512*512 * 1152 * 256 FLOPs per launch, in the operand
+    format the train step uses for it (precision.grad_fmt(): bf16 in mixed16 mode, TF32 otherwise)."""
+    from michigan_b200 import ops, precision
     dev = "cuda"
     dy = torch.randn(batch, SIZE, SIZE, 256, device=dev)
     x = torch.randn(batch, SIZE, SIZE, 128, device=dev)
-    f = lambda: ops.conv_wgrad(dy, x, 3, 3, 1, 1)
+    if precision.grad_fmt() == ops.BF16:
+        dy16, x16 = dy.bfloat16(), x.bfloat16()
+        del dy, x
+        f = lambda: ops.conv_wgrad16(dy16, x16, 3, 3, 1, 1)
+        kind = "kind::f16 (bf16 operands)"
+    else:
+        f = lambda: ops.conv_wgrad(dy, x, 3, 3, 1, 1)
+        kind = "kind::tf32"
     ms = _time_kernel(f, reps=3)
     flops = 2.0 * batch * SIZE * SIZE * 1152 * 256
-    return flops / (ms * 1e-3) / 1e12, ms, flops
+    return flops / (ms * 1e-3) / 1e12, ms, flops, kind
 
 
 # ================================================================================================ native arm
@@ -515,8 +522,8 @@ def train_step_leg(a, rank, world, local, model):
     out = {
         "metric": "512x512 images/sec (train step)", "value": world * batch * a.steps / (ms_block * 1e-3), "unit": "images/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "dtype": "forward: fp16/bf16 tensor-core operands as the generator-forward leg; gradient GEMMs: TF32 operands; fp32 accumulate, "
-                 "storage, statistics and Adam",
+        "dtype": "forward: fp16/bf16 tensor-core operands as the generator-forward leg; gradient GEMMs of the generator blocks: bf16 operands "
+                 "(encoders / discriminator: TF32); fp32 accumulate, storage, statistics and Adam",
         "config": {"workload": "full G+D train iteration (hinge GAN + GAN-feature losses, Adam TTUR), netG=spadeb ngf64, "
                                "netD=multiscale ndf64, batch %d/GPU, 512x512 synthetic" % batch,
                    "global_batch": batch * world, "parallelism": "dp%d" % world,
@@ -580,11 +587,12 @@ def run_native(a):
                 "note": "algorithmic FLOPs (one product per MAC); the split-precision form issues 3 products per MAC",
                 "ms_per_launch": wms, "flops_per_launch": wflops}
         if train is not None:
-            gtf, gms, gflops = wgrad_kernel_roofline(a.batch)
+            gtf, gms, gflops, gkind = wgrad_kernel_roofline(a.batch)
             train["roofline"] = {
-                "kernel": "wgrad_tf32_kernel (weight-gradient GEMM, SPADE gamma|beta wgrad of up_3: K = N*512*512 pixels, 256 x 1152 outputs, tcgen05 kind::tf32)",
+                "kernel": "wgrad_tf32_kernel (weight-gradient GEMM, SPADE gamma|beta wgrad of up_3: K = N*512*512 pixels, 256 x 1152 outputs, "
+                          "MN-major operands, tcgen05 %s)" % gkind,
                 "bound": "tensor", "achieved": gtf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gtf / peak_tf, "traffic": None,
-                "peak_kind": "%s bf16 dense burst; kind::tf32 issues at half the bf16 rate" % pk_kind,
+                "peak_kind": "%s bf16 dense burst (MEASURED_PEAKS.json)" % pk_kind,
                 "ms_per_launch": gms, "flops_per_launch": gflops}
         if line is None:
             line = train

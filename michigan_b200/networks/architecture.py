@@ -100,7 +100,7 @@ class SPADEResnetBlock(nn.Module):
             if self.learned_shortcut:
                 nss, nhs = self.norm_s.param_free_norm.scale_shift(x)
 
-        gfmt, gsplit = precision.gb_policy(R)
+        gfmt, gsplit = precision.gb_policy(R, self.training)
 
         def spade_act(name, src, shift, nscale, nshift, act):
             """-> (tensor-core operand (fmt, hi, lo) holding act(SPADE(src)) for the consumer conv, saved state | None)."""

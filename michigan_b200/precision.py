@@ -36,15 +36,23 @@ def gb_fmt(cin=128):
     return ops.F16 if (_mode == "mixed16" and cin % 64 == 0) else ops.TF32
 
 
-def gb_policy(ratio):
-    """(fmt, split) of the SPADE gamma/beta GEMM of a block whose feature map is 1/`ratio` of the segmap resolution.  The
-    low-resolution blocks (head_0, G_middle_0/1, up_0: ratio >= 8, 6 % of the gamma/beta FLOPs) feed every later batch-norm, so
-    their GEMMs use the three-pass bf16 split; emulation on the 512x512 net: image max-abs error 1.0e-3 -> 4.9e-4.
-    The criterion is the block's DEPTH (resolution ratio), not its absolute height: with --add_feat_zeros the same blocks run at
-    9..72 instead of 8..64 pixels (measured: keying on h <= 64 left up_0 in one-pass fp16 at 576x576 and the image error at
-    2.5e-3)."""
+def gb_policy(ratio, training=True):
+    """(fmt, split) of the SPADE gamma/beta GEMM of a block whose feature map is 1/`ratio` of the segmap resolution.
+
+    Train-mode statistics (the benchmarked forward, every training iteration): the low-resolution blocks (head_0,
+    G_middle_0/1, up_0: ratio >= 8, 6 % of the gamma/beta FLOPs) feed every later batch-norm, so their GEMMs use the three-pass
+    bf16 split, the others one-pass fp16; emulation on the 512x512 net: image max-abs error 1.0e-3 -> 4.9e-4.
+    The criterion is the block's DEPTH (resolution ratio), not its absolute height: with --add_feat_zeros the same blocks run
+    at 9..72 instead of 8..64 pixels (keying on h <= 64 left up_0 in one-pass fp16 at 576x576: 2.5e-3).
+
+    Eval mode (running statistics, inference.py): batch-norm no longer re-normalises each layer's output, so the operand rounding
+    of the one-pass GEMMs propagates instead of being absorbed by the next layer's statistics - measured on the 576x576
+    inference geometry 0.9e-3 .. 1.1e-3 max-abs (mean 2e-5) with the training policy.  Every gamma/beta GEMM therefore uses the
+    three-pass split in eval mode (single-image inference is latency-, not throughput-bound)."""
     if _mode != "mixed16":
         return ops.TF32, False
+    if not training:
+        return ops.BF16, True
     return (ops.BF16, True) if ratio >= 8 else (ops.F16, False)
 
 
@@ -57,11 +65,13 @@ def grad_fmt():
 
 
 def conv_grad_fmt():
-    """Operand format of the OTHER gradient GEMMs (conv_0 / conv_1 / conv_s, encoders, discriminator: data and weight
-    gradients).  TF32 by default; MICHIGAN_B200_GRAD16=all runs them with bf16 operands too (dY converted once per layer, the
-    forward's bf16 hi operand reused as the weight-gradient input) - an experiment, see DESIGN.md §5."""
+    """Operand format of the gradient GEMMs of conv_0 / conv_1 / conv_s (data and weight gradients): bf16 operands, fp32
+    accumulation (dY converted once per layer, the forward's bf16 hi operand reused as the weight-gradient input); measured
+    against the reference trainer's gradients: worst per-tensor cosine 0.9991 with bf16 vs 0.9989 with TF32 (the difference to
+    the reference is dominated by the piecewise-linear losses, not by operand rounding) and -3.5 % step time.
+    MICHIGAN_B200_GRAD16=gb keeps these GEMMs in TF32."""
     import os
-    return ops.BF16 if (_mode == "mixed16" and os.environ.get("MICHIGAN_B200_GRAD16", "") == "all") else ops.TF32
+    return ops.BF16 if (_mode == "mixed16" and os.environ.get("MICHIGAN_B200_GRAD16", "all") == "all") else ops.TF32
 
 
 def conv_fmt(cin):
