@@ -56,9 +56,17 @@ def _chk(t, name, dtype=torch.float32):
         raise ValueError("%s must be contiguous" % name)
 
 
+_SPADE_BN_MAX = int(os.environ.get("MG_SPADE_BN", "256"))
+# N tile of split-precision 3x3 / stride-1 convs routed to the M-tile-group kernel (0 = the launcher's default: min(Cout, 256)).
+# 64: merged accumulators of 128 columns for every such layer (double-buffered groups; weights re-read per 256 instead of 128 pixels)
+_CONV3_BN = int(os.environ.get("MG_CONV3_BN", "0"))
+
+
 def spade_bn(c):
-    """GEMM N tile used for a gamma|beta operand of `c` channels (must match the weight packing)."""
-    return 256 if 2 * c >= 256 else max(64, 2 * c)
+    """GEMM N tile used for a gamma|beta operand of `c` channels (must match the weight packing: [gamma(BN/2) | beta(BN/2)] per
+    N tile).  MG_SPADE_BN=128: 128-column tiles, which the 3x3 M-tile-group kernel can double buffer (two M tiles share every
+    weight slot: half the weight bytes through L2 per pixel, at the price of N = 128 MMAs)."""
+    return _SPADE_BN_MAX if 2 * c >= _SPADE_BN_MAX else max(64, 2 * c)
 
 
 # ------------------------------------------------------------------------------------------ weights
@@ -137,6 +145,9 @@ def conv_igemm(x, wpack, cout, kh, kw, stride=1, pad=0, *, act=ACT_NONE, round_o
     a.N, a.H, a.W, a.Cin = N, H, W, Cin
     a.OH, a.OW, a.Cout = OH, OW, cout
     a.KH, a.KW, a.stride, a.pad = kh, kw, stride, pad
+    if bn == 0 and _CONV3_BN and spade is None and x_lo is not None and kh == 3 and kw == 3 and stride == 1 and pad == 1 \
+            and OW % 16 == 0 and OH >= 16 and cout > _CONV3_BN and cout % _CONV3_BN == 0:
+        bn = _CONV3_BN
     a.BN = bn
     a.epi = EPI_SPADE if spade is not None else EPI_BIAS
     a.act, a.round_out = act, int(round_out)
