@@ -164,6 +164,9 @@ int mg_conv_to1(const float* x, const float* w_oihw, const float* bias, float* o
 /* Param-free batch-norm statistics (sync_batchnorm/batchnorm.py:63-93,128-145; F.batch_norm path
  * batchnorm.py:65-68).  sums: [2*C] doubles (sum, sum of squares), accumulated (caller zeroes).   */
 int mg_bn_stats(const float* x, long long P, int C, double* sums, void* stream);
+/* the same pass also writes a bf16 copy of x (backward: bias gradient = channel sums of dY, and dY's bf16 operand copy for the
+ * gradient GEMMs, in one read of dY) */
+int mg_bn_stats_cvt16(const float* x, long long P, int C, double* sums, void* out_bf16, void* stream);
 /* mean/var from (all-reduced) sums over `count` values -> nscale = rstd, nshift = -mean*rstd;
  * count <= 0: the sample count is read from sums[2*C] (the per-rank counts all-reduced together with the sums,
  * batchnorm.py:119 `sum_size`), so no host value depends on the other ranks' shard sizes.

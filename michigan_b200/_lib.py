@@ -73,6 +73,7 @@ SIGNATURES = {
     "mg_conv_img": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_to1": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_bn_stats": [_p, _ll, _i, _p, _p],
+    "mg_bn_stats_cvt16": [_p, _ll, _i, _p, _p, _p],
     "mg_bn_finalize": [_p, _i, _d, _d, _f, _f, _i, _p, _p, _p, _p, _p, _p, _p],
     "mg_bn_from_running": [_p, _p, _i, _f, _p, _p, _p],
     "mg_in_stats": [_p, _i, _ll, _i, _p, _p],

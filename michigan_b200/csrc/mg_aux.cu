@@ -496,7 +496,8 @@ conv_to1_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 // stride over pixels; fp32 partials are flushed to double every 32 pixels; warp-free smem reduce,
 // one double atomic per (block, channel, moment).
 __global__ void __launch_bounds__(256)
-chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __restrict__ sums, int blocks_per_b) {
+chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __restrict__ sums, int blocks_per_b,
+                  uint16_t* __restrict__ out16) {
     const int G = C / 4;                    // float4 groups
     const int tpr = G < 256 ? G : 256;      // threads per pixel row
     const int rows = 256 / tpr;
@@ -513,6 +514,11 @@ chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __res
         if (threadIdx.x < rows * tpr) {
             for (long long pidx = (long long)blk * rows + tr; pidx < P; pidx += (long long)blocks_per_b * rows) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)pidx * C) + g0);
+                if (out16) {   // bf16 copy in the same pass (operand of the 16-bit gradient GEMMs; B == 1 only)
+                    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), bb = __floats2bfloat162_rn(v.z, v.w);
+                    *reinterpret_cast<uint2*>(out16 + (size_t)pidx * C + g0 * 4) =
+                        make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&bb));
+                }
                 fs[0] += v.x; fs[1] += v.y; fs[2] += v.z; fs[3] += v.w;
                 fq[0] = fmaf(v.x, v.x, fq[0]); fq[1] = fmaf(v.y, v.y, fq[1]);
                 fq[2] = fmaf(v.z, v.z, fq[2]); fq[3] = fmaf(v.w, v.w, fq[3]);
@@ -988,7 +994,7 @@ extern "C" int mg_conv_to1(const float* x, const float* w, const float* bias, fl
     return check_launch("mg_conv_to1");
 }
 
-static int launch_stats(const float* x, int B, long long P, int C, double* sums, cudaStream_t st) {
+static int launch_stats(const float* x, int B, long long P, int C, double* sums, cudaStream_t st, uint16_t* out16 = nullptr) {
     if (C % 4 != 0 || C > 4096 || (C > 1024 && C % 1024 != 0)) return set_error(-2, "chan_stats: C %d unsupported", C);
     const int G = C / 4;
     const int tpr = G < 256 ? G : 256;
@@ -997,12 +1003,16 @@ static int launch_stats(const float* x, int B, long long P, int C, double* sums,
     long long cap = ((long long)num_sms() * 4 + B - 1) / B;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    chan_stats_kernel<<<(int)want * B, 256, 0, st>>>(x, P, C, sums, (int)want);
+    chan_stats_kernel<<<(int)want * B, 256, 0, st>>>(x, P, C, sums, (int)want, out16);
     return check_launch("chan_stats");
 }
 extern "C" int mg_bn_stats(const float* x, long long P, int C, double* sums, void* stream) {
     if (!x || !sums) return set_error(-1, "mg_bn_stats: null pointer");
     return launch_stats(x, 1, P, C, sums, ST(stream));
+}
+extern "C" int mg_bn_stats_cvt16(const float* x, long long P, int C, double* sums, void* out_bf16, void* stream) {
+    if (!x || !sums || !out_bf16) return set_error(-1, "mg_bn_stats_cvt16: null pointer");
+    return launch_stats(x, 1, P, C, sums, ST(stream), static_cast<uint16_t*>(out_bf16));
 }
 extern "C" int mg_in_stats(const float* x, int N, long long HW, int C, double* sums, void* stream) {
     if (!x || !sums) return set_error(-1, "mg_in_stats: null pointer");

@@ -59,14 +59,8 @@ def _conv_weight(conv, inv_of):
     return conv.weight, None, False
 
 
-def _grad16(t):
-    """bf16 copy of a gradient / activation tensor when the conv gradient GEMMs run in bf16 and its channels allow it."""
-    if precision.conv_grad_fmt() == ops.BF16 and t.shape[-1] % 64 == 0:
-        return ops.cvt16(t, ops.BF16)
-    return None
-
-
-def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_bias=True, dz_for_bias=None, dy16=None, a16=None):
+def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_bias=True, dz_for_bias=None, dy16=None, a16=None,
+                      bias_sum=None):
     """Weight (+bias) gradients of an implicit-GEMM conv; dy: [N,OH,OW,Cout], a_operand: its fp32 input.
     dy16 / a16: bf16 copies (both given -> bf16 weight-gradient GEMM)."""
     w, isg, is_sn = _conv_weight(conv, inv_of)
@@ -82,14 +76,20 @@ def _conv_param_grads(G, conv, inv_of, dy, a_operand, kh, kw, stride, pad, with_
     else:
         G.add(w, dwt)
     if with_bias and getattr(conv, "bias", None) is not None:
-        G.add(conv.bias, ops.chan_sum(dz_for_bias if dz_for_bias is not None else dy))
+        G.add(conv.bias, bias_sum if bias_sum is not None else ops.chan_sum(dz_for_bias if dz_for_bias is not None else dy))
 
 
 # =============================================================================================== SPADE + conv
 def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     """Backward of conv(act(SPADE(src))) given dy; returns (dxhat, sums) for the BN backward of `src`."""
-    dy16 = _grad16(dy)
-    _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad, dy16=dy16, a16=getattr(S, "h16", None))
+    # bf16 gradient GEMMs: dY's bf16 copy and (for convs with a bias) its channel sums come out of one pass over dY
+    dy16 = bias_sum = None
+    if precision.conv_grad_fmt() == ops.BF16 and dy.shape[-1] % 64 == 0:
+        if getattr(conv, "bias", None) is not None:
+            bias_sum, dy16 = ops.chan_sum_cvt16(dy)
+        else:
+            dy16 = ops.cvt16(dy, ops.BF16)
+    _conv_param_grads(G, conv, inv_of, dy, S.h, k, k, 1, pad, dy16=dy16, a16=getattr(S, "h16", None), bias_sum=bias_sum)
     w, isg, _ = _conv_weight(conv, inv_of)
     dh = ops.conv_dgrad(dy, w.detach(), S.hw, 1, pad, inv_sigma=isg, dy16=dy16)
     del dy16

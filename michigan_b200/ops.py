@@ -296,6 +296,16 @@ def bn_sums(x):
     return sums
 
 
+def chan_sum_cvt16(x):
+    """-> (per-channel sums [C] fp32, bf16 copy of x) in ONE pass over x (bias gradient + gradient-GEMM operand)."""
+    _chk(x, "x")
+    Cc = x.shape[-1]
+    sums = torch.zeros(2 * Cc + 1, device=x.device, dtype=torch.float64)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().mg_bn_stats_cvt16(_p(x), x.numel() // Cc, Cc, _p(sums), _p(out), _stream()), "mg_bn_stats_cvt16")
+    return sums[:Cc].float(), out
+
+
 def bn_finalize(sums, count, unbiased_mult=1, eps=1e-5, momentum=0.1, clamp_mode=0, running_mean=None, running_var=None,
                 want_stats=False):
     """count: number of samples behind `sums`, or 0.0 = read the all-reduced count from sums[2*C] on the device;

@@ -232,6 +232,9 @@ def test_wgrad_bf16_operands(gen, N, h, Cin, Cout, k, s, p):
     dw = ops.unpack_wgrad(dwp, tuple(w.shape))
     assert rel_err(dw, w.grad) <= 5e-5
     assert torch.equal(ops.cvt16(nhwc(dy)), nhwc(dy).bfloat16())
+    sums, d16 = ops.chan_sum_cvt16(nhwc(dy))
+    assert torch.equal(d16, nhwc(dy).bfloat16())
+    assert rel_err(sums, dy.sum(dim=(0, 2, 3))) <= 1e-5
 
 
 @pytest.mark.parametrize("fmt", ["tf32", "f16", "bf3"])
