@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="both", choices=["both", "gen_fwd", "train_step"])
+    ap.add_argument("--workload", default="both", choices=["both", "gen_fwd", "train_step", "train_step_ig"],
+                    help="both (default) = generator forward + train step in one line; train_step_ig = BASELINE.json configs[4]'s "
+                         "per-GPU work: the train step with --use_ig (frozen orientation-inpainting net, run twice per iteration)")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -459,7 +461,7 @@ def gen_fwd_leg(a, rank, world, local, model):
     }
 
 
-def train_step_leg(a, rank, world, local, model):
+def train_step_leg(a, rank, world, local, model, use_ig=False):
     """BASELINE.json configs[2]: one generator update + one discriminator update per step (train.py:94-101)."""
     import torch.distributed as dist
     from michigan_b200 import _lib
@@ -469,7 +471,7 @@ def train_step_leg(a, rank, world, local, model):
     batch = a.batch
     wrap = DataParallelWithCallback(model, device_ids=[local])
     optG, optD = model.create_optimizers(model.opt)
-    data = synthetic_batch(batch, SIZE, 1234 + rank)
+    data = synthetic_batch(batch, SIZE, 1234 + rank, use_ig=use_ig)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
     last = {}
@@ -517,21 +519,25 @@ def train_step_leg(a, rank, world, local, model):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     t_e2e = t_e2e.item()
-    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v) and k in INPUT_KEYS) * 2   # G step + D step
+    keys = INPUT_KEYS + (("hole", "orient_rgb") if use_ig else ())
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v) and k in keys) * 2   # G step + D step
     ms_step = ms_block / a.steps
     out = {
-        "metric": "512x512 images/sec (train step)", "value": world * batch * a.steps / (ms_block * 1e-3), "unit": "images/s",
+        "metric": "512x512 images/sec (train step%s)" % (", --use_ig" if use_ig else ""), "value": world * batch * a.steps / (ms_block * 1e-3),
+        "unit": "images/s", "vs_baseline": None, "data": "synthetic",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "dtype": "forward: fp16/bf16 tensor-core operands as the generator-forward leg; gradient GEMMs of the generator blocks: bf16 operands "
                  "(encoders / discriminator: TF32); fp32 accumulate, storage, statistics and Adam",
         "config": {"workload": "full G+D train iteration (hinge GAN + GAN-feature losses, Adam TTUR), netG=spadeb ngf64, "
                                "netD=multiscale ndf64, batch %d/GPU, 512x512 synthetic" % batch,
                    "global_batch": batch * world, "parallelism": "dp%d" % world,
-                   "l2": "no explicit flush: multi-GB activations per step", "algorithmic_gflop_per_image": TRAIN_GFLOP_PER_IMG,
+                   "l2": "no explicit flush: multi-GB activations per step",
+                   "algorithmic_gflop_per_image": TRAIN_GFLOP_PER_IMG + (2 * 151.9 if use_ig else 0.0),
+                   "use_ig": bool(use_ig),
                    "timing": "median of %d blocks of %d steps" % (len(blocks), a.steps),
                    "syncbn_exchange": exchange_backend(), "grad_allreduce": "in-backward staged NCCL all-reduce (AVG) of a flat fp32 buffer"},
         "blocks_ms": blocks,
-        "achieved_tflops_step": TRAIN_GFLOP_PER_IMG * batch / ms_step,
+        "achieved_tflops_step": (TRAIN_GFLOP_PER_IMG + (2 * 151.9 if use_ig else 0.0)) * batch / ms_step,
         "e2e": {"value": world * batch * e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * nl,
                 "steps": e2e_steps,
                 "how": "train_iteration(DataParallelWithCallback(Pix2PixModel), ...) per step from pinned host tensors; the loss "
@@ -555,7 +561,19 @@ def run_native(a):
     from michigan_b200.synth import fill_state_dict
 
     torch.manual_seed(0)
-    opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world, niter=50, niter_decay=0)
+    use_ig = a.workload == "train_step_ig"
+    extra = {}
+    if use_ig:
+        # a random-init InpaintingModel_gen.pth in the reference's layout ({'generator': state_dict}, util.py:245-257)
+        import tempfile
+        from michigan_b200.networks import InpaintGenerator
+        ckdir = os.path.join(tempfile.gettempdir(), "mg_bench_ig_%d" % os.getpid())
+        os.makedirs(os.path.join(ckdir, "MichiGAN"), exist_ok=True)
+        ig = InpaintGenerator()
+        fill_state_dict(ig.state_dict(), 2)
+        torch.save({"generator": ig.state_dict()}, os.path.join(ckdir, "MichiGAN", "InpaintingModel_gen.pth"))
+        extra = dict(use_ig=True, checkpoints_dir=ckdir, name="MichiGAN", ig_model_name="InpaintingModel_gen.pth", netIG="inpaint")
+    opt = make_opt(is_train=True, gpu_ids=[local], batchSize=a.batch * world, niter=50, niter_decay=0, **extra)
     model = Pix2PixModel(opt)
     fill_state_dict(model.netG.state_dict(), 0)  # random-init weights of the reference architecture (109.5 M params)
     fill_state_dict(model.netD.state_dict(), 1)
@@ -565,8 +583,8 @@ def run_native(a):
     if a.workload in ("both", "gen_fwd"):
         line = gen_fwd_leg(a, rank, world, local, model)
     train = None
-    if a.workload in ("both", "train_step"):
-        train = train_step_leg(a, rank, world, local, model)
+    if a.workload in ("both", "train_step", "train_step_ig"):
+        train = train_step_leg(a, rank, world, local, model, use_ig)
     if rank == 0:
         pk, pk_kind = peaks()
         peak_tf = float(pk["bf16_tflops"])

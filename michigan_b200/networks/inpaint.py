@@ -141,9 +141,7 @@ class InpaintGenerator(BaseNetwork):
         """x: [N,4,H,W] fp32 CUDA (orientation RGB with the hole filled by noise + hole mask) -> [N,3,H,W] in [0,1]."""
         if self.training:
             raise RuntimeError("InpaintGenerator is a frozen network: call .eval() (pix2pix_model.py:196-198)")
-        if not x.is_cuda:
-            raise ops._lib.MichiganNativeError("InpaintGenerator has no CPU path")
-        return self._forward_impl(x)
+        return self._forward_impl(x)      # every op below rejects CPU tensors (ops._chk): there is no CPU path
 
     def _forward_impl(self, x):
         enc, mid, dec = self.encoder, self.middle, self.decoder

@@ -97,6 +97,13 @@ class Pix2PixModel(torch.nn.Module):
         o2 = (out[:, :-1] - 0.5) * 2
         return out, (torch.stack([o2[:, 1], o2[:, 0]], dim=1) * mask).contiguous()
 
+    def train(self, mode=True):
+        """The orientation-inpainting net is frozen: it stays in eval mode whatever the model's mode (pix2pix_model.py:196-198)."""
+        super().train(mode)
+        if self.netIG is not None:
+            self.netIG.eval()
+        return self
+
     # ------------------------------------------------------------------ entry point
     def forward(self, data, mode):
         input_ref, input_tag, image_ref, image_tag, orient_mask, noise = self.preprocess_input(data)

@@ -110,3 +110,28 @@ def test_standalone_model_train_iteration_glue(tmp_path):
         assert list(sd.keys()) == list(model.netG.state_dict().keys())
         out = model(dict(data), mode="inference")
         assert tuple(out.shape) == (2, 3, 64, 64) and not out.requires_grad
+
+
+def test_use_ig_and_orientation_loss_glue(tmp_path):
+    """BASELINE.json configs[4]'s model: --use_ig (frozen InpaintGenerator loaded from <checkpoints_dir>/<name>/InpaintingModel_gen.pth,
+    2-channel orientation input derived from its output) plus the Gabor orientation / confidence losses."""
+    import os
+    from michigan_b200.networks import InpaintGenerator
+    from michigan_b200.options import make_opt
+    from michigan_b200.pix2pix_model import Pix2PixModel, train_iteration
+    from michigan_b200.synth import fill_state_dict, synthetic_batch
+    os.makedirs(tmp_path / "ig")
+    ig = InpaintGenerator()
+    fill_state_dict(ig.state_dict(), 2)
+    torch.save({"generator": ig.state_dict()}, tmp_path / "ig" / "InpaintingModel_gen.pth")
+    with dry_run():
+        opt = make_opt(is_train=True, ngf=64, ndf=64, crop_size=256, batchSize=1, use_ig=True, checkpoints_dir=str(tmp_path), name="ig",
+                       ig_model_name="InpaintingModel_gen.pth", netIG="inpaint", no_orient_loss=False, no_confidence_loss=False)
+        model = Pix2PixModel(opt).train()
+        assert not model.netIG.training and model.netG.training
+        optG, optD = model.create_optimizers(opt)
+        assert len(list(optG.param_groups[0]["params"])) == len(list(model.netG.parameters()))      # the frozen net is not optimised
+        data = synthetic_batch(1, 256, 3, use_ig=True)
+        random.seed(0)
+        g, d, img = train_iteration(model, optG, optD, dict(data))
+        assert set(g) == {"GAN", "GAN_Feat", "ORIENT", "CONFIDENCE"} and tuple(img.shape) == (1, 3, 256, 256)

@@ -427,3 +427,38 @@ def test_inpaint_generator_vs_oracle():
     mx, mn = max_mean_abs(out, ref)
     print("InpaintGenerator vs oracle: max-abs %.3e mean-abs %.3e" % (mx, mn))
     assert mx <= MAX_ABS
+
+
+def test_use_ig_train_iteration_vs_oracle_orientation_input(tmp_path):
+    """BASELINE.json configs[4]'s model path: --use_ig.  The 2-channel orientation input the generator receives
+    (Pix2PixModel.inpainting_orient, pix2pix_model.py:407-429: nearest 512->256, frozen InpaintGenerator, nearest back,
+    hole blend, channel swap, hair mask) against the oracle, then one full train iteration with the orientation /
+    confidence losses switched on (finite losses, gradients for every generator parameter)."""
+    from michigan_b200.networks import InpaintGenerator
+    from michigan_b200.options import make_opt
+    from michigan_b200.pix2pix_model import Pix2PixModel, train_iteration
+    from michigan_b200.synth import fill_state_dict, synthetic_batch
+    os.makedirs(tmp_path / "ig")
+    ig = InpaintGenerator()
+    fill_state_dict(ig.state_dict(), 2)
+    sd_ig = {k: v.clone() for k, v in ig.state_dict().items()}
+    torch.save({"generator": sd_ig}, tmp_path / "ig" / "InpaintingModel_gen.pth")
+    opt = make_opt(is_train=True, ngf=64, ndf=64, crop_size=512, batchSize=2, use_ig=True, checkpoints_dir=str(tmp_path), name="ig",
+                   ig_model_name="InpaintingModel_gen.pth", netIG="inpaint", no_orient_loss=False, no_confidence_loss=False)
+    model = Pix2PixModel(opt).train()
+    assert not model.netIG.training
+    data = synthetic_batch(2, 512, 3, use_ig=True)
+    hair = data["label_tag"]
+    with torch.no_grad():
+        _, o2 = model.inpainting_orient(data["hole"].cuda(), data["orient_rgb"].cuda(), data["noise"].cuda(), hair.cuda())
+        _, o2_ref = orc.inpainting_orient(sd_ig, 512, data["hole"], data["orient_rgb"], data["noise"], hair)
+    mx, mn = max_mean_abs(o2, o2_ref)
+    print("inpainting_orient (2-channel orientation input) vs oracle: max-abs %.3e mean-abs %.3e" % (mx, mn))
+    assert mx <= 2e-3           # (out - 0.5) * 2 doubles the InpaintGenerator's 1e-3 bound
+    optG, optD = model.create_optimizers(opt)
+    random.seed(0)
+    g, d, img = train_iteration(model, optG, optD, dict(data))
+    vals = {k: float(v.detach().mean()) for k, v in {**g, **d}.items()}
+    print("use_ig train iteration losses:", vals)
+    assert set(g) == {"GAN", "GAN_Feat", "ORIENT", "CONFIDENCE"} and all(np.isfinite(v) for v in vals.values())
+    assert all(torch.isfinite(p).all() for p in model.netG.parameters())
