@@ -498,29 +498,52 @@ def train_step_leg(a, rank, world, local, model, use_ig=False):
     clocks = sampler.stop() if rank == 0 else None
     ms_block = median(blocks)
 
-    # ---- end to end: every step starts from pinned HOST tensors (H2D inside) and ends with the loss scalars on the host
-    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    # ---- end to end: every step's inputs come from pinned HOST tensors (copied on a second stream into one of two device
+    # buffers while the previous step computes - a prefetching loader) and every step ends with its loss scalars read back to the
+    # host and a stream synchronisation
+    loss_host = torch.empty(8, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    tensor_keys = [k for k, v in host.items() if torch.is_tensor(v)]
+    dev_sets = [{k: torch.empty_like(host[k], device="cuda") for k in tensor_keys} for _ in range(2)]
 
-    def e2e_step():
-        g, d, _ = train_iteration(wrap, optG, optD, dict(host))
-        vals = torch.stack([v.mean() for v in {**g, **d}.values()])
-        loss_host[: vals.numel()].copy_(vals, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return vals.numel()
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            for k in tensor_keys:
+                dev_sets[i & 1][k].copy_(host[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        d = dict(host)
+        d.update(dev_sets[i & 1])
+        return d, ev
 
-    e2e_step()
+    def e2e_run(nsteps):
+        nxt = prefetch(0)
+        nl = 0
+        for i in range(nsteps):
+            d, ev = nxt
+            main_stream.wait_event(ev)
+            if i + 1 < nsteps:
+                nxt = prefetch(i + 1)        # buffer (i+1)&1 was last read by step i-1, which has been synchronised
+            g, dl, _ = train_iteration(wrap, optG, optD, d)
+            vals = torch.stack([v.detach().mean() for v in {**g, **dl}.values()])
+            nl = vals.numel()
+            loss_host[:nl].copy_(vals, non_blocking=True)
+            main_stream.synchronize()
+        return nl
+
+    e2e_run(2)
     e2e_steps = a.steps
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nl = e2e_step()
+    nl = e2e_run(e2e_steps)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     t_e2e = t_e2e.item()
     keys = INPUT_KEYS + (("hole", "orient_rgb") if use_ig else ())
-    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v) and k in keys) * 2   # G step + D step
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if torch.is_tensor(v) and k in keys)
     ms_step = ms_block / a.steps
     out = {
         "metric": "512x512 images/sec (train step%s)" % (", --use_ig" if use_ig else ""), "value": world * batch * a.steps / (ms_block * 1e-3),
@@ -540,8 +563,8 @@ def train_step_leg(a, rank, world, local, model, use_ig=False):
         "achieved_tflops_step": (TRAIN_GFLOP_PER_IMG + (2 * 151.9 if use_ig else 0.0)) * batch / ms_step,
         "e2e": {"value": world * batch * e2e_steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * nl,
                 "steps": e2e_steps,
-                "how": "train_iteration(DataParallelWithCallback(Pix2PixModel), ...) per step from pinned host tensors; the loss "
-                       "scalars are copied to pinned host memory and the stream is synchronised every step; wall clock"},
+                "how": "train_iteration(DataParallelWithCallback(Pix2PixModel), ...) per step; inputs pinned host -> device every step on a "
+                       "second stream (double-buffered), loss scalars -> pinned host and a stream synchronisation every step; wall clock"},
         "gpu_launches": launches, "clocks": clocks, "host_enqueue_ms_per_step": host_ms,
         "losses": {k: float(v.detach().mean()) for k, v in last["losses"].items()},
     }
