@@ -283,7 +283,9 @@ int mg_in_bwd(const float* df, const float* x, const float* ss, double* sums, fl
 /* thin conv gradients: dwt [KH*KW][CinP][Cout] (zeroed here); dimg_nchw [N,3,H,W] += data gradient of input
  * channels [c_lo, c_lo+3) (the generated image inside the discriminator input). */
 int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N, int H, int W, int CinP, int OH, int OW, int Cout, int KH,
-                  int KW, int stride, int pad, int pad_mode, int seg_resize, void* stream);
+                  int KW, int stride, int pad, int pad_mode, int seg_resize, const float* relu_src, double* bias_sums, void* stream);
+/* (relu_src != null: dz is first multiplied by [relu_src > 0] - the ReLU backward of SPADE's mlp_shared fused in;
+ *  bias_sums != null: [Cout] doubles += per-channel sums of that dz = the conv's bias gradient; both save a full pass over dz.) */
 int mg_thin_dgrad3(const float* dz, const float* wt, float* dimg_nchw, int N, int H, int W, int CinP, int OH, int OW, int Cout,
                    int KH, int KW, int stride, int pad, int c_lo, void* stream);
 /* conv_img backward: dx [N,H,W,Cin], dw [Cout,Cin,3,3] and db [Cout] are ACCUMULATED (zero them first). */

@@ -98,7 +98,7 @@ SIGNATURES = {
     "mg_blend_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "mg_act_bwd": [_p, _p, _p, _ll, _i, _i, _p, _p, _i, _p],
     "mg_in_bwd": [_p, _p, _p, _p, _p, _i, _ll, _i, _i, _p, _i, _p],
-    "mg_thin_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mg_thin_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "mg_thin_dgrad3": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_img_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mg_conv_to1_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],

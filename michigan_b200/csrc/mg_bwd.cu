@@ -362,7 +362,7 @@ template <int KPT>
 __global__ void __launch_bounds__(256)
 thin_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ dwt, int N, int H, int W,
                    int CinP, int OH, int OW, int Cout, int KH, int KW, int s, int pad, int pad_mode, int R, int tiles_w,
-                   int tiles_h, int num_tiles) {
+                   int tiles_h, int num_tiles, const float* __restrict__ relu_src, double* __restrict__ bias_sums) {
     extern __shared__ __align__(16) float sm[];
     const int PH = 7 * s + KH, PW = 15 * s + KW;
     float* in_s = sm;                                 // [PH][PW][CinP]
@@ -381,6 +381,9 @@ thin_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dz, fl
     float acc[KPT][4];
 #pragma unroll
     for (int i = 0; i < KPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    // fused ReLU backward + bias gradient (relu_src = the conv's forward output y: dz <- dz * [y > 0]; bias_sums[c] += sum dz):
+    // 256 % G == 0, so a thread stages the same channel group for every pixel and keeps its partial sum in registers
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tw = tile % tiles_w;
         const int th = (tile / tiles_w) % tiles_h;
@@ -408,7 +411,15 @@ thin_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dz, fl
             const int c4 = i % G, pp = i / G;
             const int oh = oh0 + (pp >> 4), ow = ow0 + (pp & 15);
             float4 v = make_float4(0, 0, 0, 0);
-            if (oh < OH && ow < OW) v = __ldg(reinterpret_cast<const float4*>(dz + (((size_t)n * OH + oh) * OW + ow) * Cout + c4 * 4));
+            if (oh < OH && ow < OW) {
+                const size_t off = (((size_t)n * OH + oh) * OW + ow) * Cout + c4 * 4;
+                v = __ldg(reinterpret_cast<const float4*>(dz + off));
+                if (relu_src) {
+                    const float4 y = __ldg(reinterpret_cast<const float4*>(relu_src + off));
+                    v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f; v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+                }
+                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+            }
             *reinterpret_cast<float4*>(dz_s + (size_t)pp * Cout + c4 * 4) = v;
         }
         __syncthreads();
@@ -433,6 +444,11 @@ thin_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dz, fl
             float* dst = dwt + (size_t)k * Cout + g * 4;
             atomicAdd(dst, acc[i][0]); atomicAdd(dst + 1, acc[i][1]); atomicAdd(dst + 2, acc[i][2]); atomicAdd(dst + 3, acc[i][3]);
         }
+    }
+    if (bias_sums && (256 % G) == 0) {
+        const int c4 = threadIdx.x % G;
+        atomicAdd(bias_sums + c4 * 4, (double)bsum.x); atomicAdd(bias_sums + c4 * 4 + 1, (double)bsum.y);
+        atomicAdd(bias_sums + c4 * 4 + 2, (double)bsum.z); atomicAdd(bias_sums + c4 * 4 + 3, (double)bsum.w);
     }
 }
 
@@ -969,7 +985,8 @@ extern "C" int mg_in_bwd(const float* df, const float* x, const float* ss, doubl
     return check_launch("mg_in_bwd");
 }
 extern "C" int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N, int H, int W, int CinP, int OH, int OW, int Cout, int KH,
-                             int KW, int stride, int pad, int pad_mode, int seg_resize, void* stream) {
+                             int KW, int stride, int pad, int pad_mode, int seg_resize, const float* relu_src, double* bias_sums,
+                             void* stream) {
     if (!x || !dz || !dwt) return set_error(-1, "mg_thin_wgrad: null pointer");
     if (Cout > 256 || 256 % Cout != 0) return set_error(-2, "mg_thin_wgrad: Cout must divide 256");
     const int K = KH * KW * CinP, parts = 256 / Cout;
@@ -996,7 +1013,7 @@ extern "C" int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N,
         cudaError_t e = cudaFuncSetAttribute(thin_wgrad2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
         if (e != cudaSuccess) return set_error((int)e, "thin_wgrad2 attr: %s", cudaGetErrorString(e));                           \
         thin_wgrad2_kernel<KP><<<grid, 256, smem, ST(stream)>>>(x, dz, dwt, N, H, W, CinP, OH, OW, Cout, KH, KW, stride, pad,    \
-                                                                pad_mode, R, tiles_w, tiles_h, num_tiles);                        \
+                                                                pad_mode, R, tiles_w, tiles_h, num_tiles, relu_src, bias_sums);   \
     } while (0)
         if (kpt <= 3) MG_TW2(3);
         else if (kpt <= 5) MG_TW2(5);
@@ -1005,6 +1022,7 @@ extern "C" int mg_thin_wgrad(const float* x, const float* dz, float* dwt, int N,
 #undef MG_TW2
         return check_launch("mg_thin_wgrad");
     }
+    if (relu_src || bias_sums) return set_error(-4, "mg_thin_wgrad: the fused ReLU / bias-sum form needs the register-tiled kernel (Cout 64 | 128)");
     if ((K + parts - 1) / parts > 64) return set_error(-3, "mg_thin_wgrad: K %d too large for %d parts", K, parts);
     const size_t smem = ((size_t)PH * PW * CinP + 128 * (size_t)Cout) * 4;
     cudaError_t e = cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -115,9 +115,9 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
     G.add(sp.mlp_gamma.bias, bsum[:c].float())
     G.add(sp.mlp_beta.bias, bsum[c:].float())
     del dgb
-    da = ops.act_bwd(dactv, actv, _RELU)
-    del dactv, actv
     if ops.thin_wgrad_tc_enabled():
+        da = ops.act_bwd(dactv, actv, _RELU)
+        del dactv, actv
         seg32 = seg_cache.get(S.R) if seg_cache is not None else None
         if seg32 is None:
             seg32 = ops.pad_channels32(seg4, seg_resize=S.R, in_hw=S.hw)
@@ -125,10 +125,13 @@ def _spade_conv_bwd(G, blk, S, conv, inv_of, dy, k, pad, seg4, seg_cache=None):
                 seg_cache.clear()          # one resolution at a time is alive (blocks run coarse -> fine in reverse)
                 seg_cache[S.R] = seg32
         dwt = ops.thin_wgrad_tc(seg32, da, 3, 3, 1, 1, 4)
+        db = ops.chan_sum(da)
     else:
-        dwt = ops.thin_wgrad(seg4, da, 3, 3, 1, 1, seg_resize=S.R, in_hw=S.hw)
+        # ReLU backward of mlp_shared and its bias gradient are fused into the weight-gradient kernel: d actv is read once
+        dwt, db = ops.thin_wgrad(seg4, dactv, 3, 3, 1, 1, seg_resize=S.R, in_hw=S.hw, relu_src=actv, want_bias=True)
+        del dactv, actv
     G.add(sp.mlp_shared[0].weight, _thin_wt_to_oihw(dwt, 3, 3, 4))
-    G.add(sp.mlp_shared[0].bias, ops.chan_sum(da))
+    G.add(sp.mlp_shared[0].bias, db)
     return dxhat, sums, allreduce_sums(sums, dxhat.numel() // c)
 
 

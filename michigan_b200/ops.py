@@ -666,16 +666,21 @@ def thin_wgrad_tc(x32, dz, kh, kw, stride, pad, cinp):
     return dwp.view(cout, kh * kw, 32)[:, :, :cinp].permute(1, 2, 0).contiguous()
 
 
-def thin_wgrad(x, dz, kh, kw, stride, pad, pad_mode=0, seg_resize=0, in_hw=None):
+def thin_wgrad(x, dz, kh, kw, stride, pad, pad_mode=0, seg_resize=0, in_hw=None, relu_src=None, want_bias=False):
     """dwt [kh*kw][CinP][Cout] of a thin conv; x is the (possibly full-resolution seg) input.
-    Register-tiled CUDA-core kernel (4 output channels x <= 13 weight columns per thread)."""
-    _chk(x, "x"); _chk(dz, "dz")
+    Register-tiled CUDA-core kernel (4 output channels x <= 13 weight columns per thread).
+    relu_src: the conv's forward output y - dz is multiplied by [y > 0] on the fly (ReLU backward fused in);
+    want_bias: also return the per-channel sums of that dz (the bias gradient) -> (dwt, bias[Cout] fp32)."""
+    _chk(x, "x"); _chk(dz, "dz"); _chk(relu_src, "relu_src")
     N, OH, OW, Cout = dz.shape
     CinP = x.shape[-1]
     H, W = in_hw if seg_resize else (x.shape[1], x.shape[2])
     dwt = torch.empty((kh * kw, CinP, Cout), device=x.device, dtype=torch.float32)
+    bsum = torch.zeros(Cout, device=x.device, dtype=torch.float64) if want_bias else None
     check(_lib.load().mg_thin_wgrad(_p(x), _p(dz), _p(dwt), N, H, W, CinP, OH, OW, Cout, kh, kw, stride, pad, pad_mode, seg_resize,
-                                    _stream()), "mg_thin_wgrad")
+                                    _p(relu_src), _p(bsum), _stream()), "mg_thin_wgrad")
+    if want_bias:
+        return dwt, bsum.float()
     return dwt
 
 

@@ -201,6 +201,24 @@ def test_thin_wgrad_vs_autograd(gen, Cin, CinP, Cout, k, s, p, pm):
     assert rel_err(dw, w.grad) <= 2e-5
 
 
+def test_thin_wgrad_fused_relu_backward_and_bias(gen):
+    """SPADE mlp_shared backward in one kernel: d actv * [actv > 0] applied on the fly, weight gradient over the nearest-resized
+    segmap and the bias gradient (per-channel sums), against torch autograd of relu(conv3x3(resize(seg)))."""
+    ops = _ops()
+    N, hs, R = 2, 24, 2
+    seg = torch.randn(N, 4, hs * R, hs * R, generator=gen).to(dev)
+    w = (torch.randn(128, 4, 3, 3, generator=gen) / 6).to(dev).requires_grad_(True)
+    b = (torch.randn(128, generator=gen) * 0.1).to(dev).requires_grad_(True)
+    seg_r = seg[:, :, ::R, ::R]                                  # nearest resize to hs x hs (integer ratio: floor(dst * R))
+    actv = F.relu(F.conv2d(seg_r, w, b, padding=1))
+    dact = torch.randn(actv.shape, generator=gen).to(dev)
+    actv.backward(dact)
+    dwt, db = ops.thin_wgrad(nhwc(seg), nhwc(dact), 3, 3, 1, 1, seg_resize=R, in_hw=(hs, hs), relu_src=nhwc(actv.detach()), want_bias=True)
+    dw = dwt.view(3, 3, 4, 128).permute(3, 2, 0, 1)
+    assert rel_err(dw, w.grad) <= 2e-5
+    assert rel_err(db, b.grad) <= 2e-5
+
+
 @pytest.mark.parametrize("N,h,Cin,Cout,k,s,p", [(2, 32, 64, 64, 3, 1, 1), (2, 33, 64, 128, 4, 2, 2), (3, 8, 128, 64, 1, 1, 0), (2, 32, 64, 128, 3, 2, 1)])
 def test_tensor_core_wgrad_and_dgrad(gen, N, h, Cin, Cout, k, s, p):
     """wgrad (both operands MN-major from NHWC, one filter row per CTA) and dgrad (the forward kernel on dY with per-parity
