@@ -6,6 +6,7 @@ written TF32-rounded by their producer; the 2x nearest upsamples (generator.py:7
 hair/background mask pyramids (generator.py:149-159, encoder.py:332-336) are never materialised -
 consumers index the low-resolution tensor / full-resolution mask directly.
 """
+import os
 from types import SimpleNamespace
 
 import torch
@@ -15,6 +16,9 @@ from .architecture import SPADEResnetBlock
 from .base_network import BaseNetwork
 from .encoder import BackgroundEncode2, ImageEncoder3
 from .prep import PackCache, SpectralNormBatch
+
+# MICHIGAN_B200_OVERLAP=0: background encoder on the main stream (no second stream)
+_OVERLAP = os.environ.get("MICHIGAN_B200_OVERLAP", "1") != "0"
 
 
 class SPADEBGenerator(BaseNetwork):
@@ -76,6 +80,14 @@ class SPADEBGenerator(BaseNetwork):
         return [ps(self.conv_img, self.up_3, self.up_2, self.up_1), ps(self.up_0), ps(self.G_middle_1), ps(self.G_middle_0),
                 ps(self.head_0), ps(self.fc, self.backgroud_enc)]
 
+    def _side_stream(self):
+        dev = torch.cuda.current_device()
+        st = getattr(self, "_side", None)
+        if st is None or st.device.index != dev:
+            st = torch.cuda.Stream(device=dev)
+            self._side = st
+        return st
+
     def spectral_batch(self):
         if self._snb is None:
             convs = []
@@ -110,8 +122,20 @@ class SPADEBGenerator(BaseNetwork):
         ins_tag = input_tag[:, 1:2]
         sv = (lambda: SimpleNamespace()) if save is not None else (lambda: None)
         Sfc, Sbg = sv(), sv()
+        # The background encoder (generator.py:144-147; full-resolution maps, 148-CTA kernels) is independent of the reference
+        # encoder and of head_0 / G_middle_0 / G_middle_1, whose 8x8..32x32 maps give the persistent GEMM kernels only 16..128 tiles:
+        # it runs on a second stream and fills the SMs those kernels leave idle; the main stream joins before up_0's blend.
+        overlap = _OVERLAP and input_tag.is_cuda
+        if overlap:
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_event(main.record_event())
+            with torch.cuda.stream(side):
+                feats, back = self.backgroud_enc.forward_nhwc(image_tag, input_tag, noise, save=Sbg)
+                bg_done = side.record_event()
+        else:
+            feats, back = self.backgroud_enc.forward_nhwc(image_tag, input_tag, noise, save=Sbg)  # generator.py:144-147
         x = self.fc.forward_nhwc(image_ref, ins_ref, ins_tag, save=Sfc)              # generator.py:117-123
-        feats, back = self.backgroud_enc.forward_nhwc(image_tag, input_tag, noise, save=Sbg)  # generator.py:144-147
         hair = input_tag[:, 1].contiguous()
         snb = self.spectral_batch()
         inv = snb.run(self.training)
@@ -129,6 +153,8 @@ class SPADEBGenerator(BaseNetwork):
             if idx < 3:
                 x = blk.forward_nhwc(x, 0 if idx == 0 else 1, seg4, inv_of, save=S)
             else:
+                if overlap and idx == 3:
+                    main.wait_event(bg_done)
                 i = idx - 3
                 ms = 8 >> i  # hair_masks / back_masks pyramid level == stride into the full-resolution masks
                 x = blk.forward_nhwc(x, 1, seg4, inv_of, blend=(feats[i], hair, back, ms), save=S)
