@@ -41,6 +41,8 @@ class SPADEBGenerator(BaseNetwork):
             raise NotImplementedError("michigan_b200: num_upsampling_layers must be 'more' (the default)")
         if getattr(opt, "no_orientation", False):
             raise NotImplementedError("michigan_b200: the orientation map is required")
+        if getattr(opt, "bf_direct_add", False):
+            raise NotImplementedError("michigan_b200: --bf_direct_add is not implemented")
         self.fc = ImageEncoder3(opt, self.sw, self.sh)
         self.head_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
         self.G_middle_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
