@@ -17,8 +17,10 @@ from .base_network import BaseNetwork
 from .encoder import BackgroundEncode2, ImageEncoder3
 from .prep import PackCache, SpectralNormBatch
 
-# MICHIGAN_B200_OVERLAP=0: background encoder on the main stream (no second stream)
-_OVERLAP = os.environ.get("MICHIGAN_B200_OVERLAP", "1") != "0"
+# MICHIGAN_B200_OVERLAP=1: background encoder on a second stream.  Measured same-box (profiles/r02_ab_overlap.log): 23.04 vs 22.99 ms
+# per forward, i.e. nothing - the low-resolution blocks are short and the encoder's 148-CTA kernels cannot share an SM with a
+# 227 KB-smem GEMM CTA anyway - so it stays off.
+_OVERLAP = os.environ.get("MICHIGAN_B200_OVERLAP", "0") == "1"
 
 
 class SPADEBGenerator(BaseNetwork):
