@@ -278,7 +278,7 @@ def _cosine(got_summary, ref_summary):
 def test_backward_chain_smooth_loss_vs_oracle():
     """Whole backward chain (generator -> discriminator) with a SMOOTH loss, against torch autograd on the
     CPU oracle: L = sum over the 10 discriminator outputs of mean(out^2).  Every parameter gradient of G and
-    D is compared in relative L2.  Bound: 0.2.  The forward runs with TF32 operands (features accurate to
+    D is compared in relative L2.  Bound: 0.1 (measured <= 4e-2; round 1: 0.2).  The forward runs with TF32 operands (features accurate to
     ~5e-4), and LeakyReLU / ReLU derivatives jump at 0, so ~0.05 % of the activation-derivative masks differ
     from the fp32 oracle per layer: measured ~2e-2 per discriminator layer, ~1e-2 per SPADE block, compounding
     to ~0.12 at the reference encoder (7 blocks upstream); single-block and single-kernel gradients are checked
@@ -341,15 +341,15 @@ def test_backward_chain_smooth_loss_vs_oracle():
         print("   %s: largest relative L2 gradient errors (gmax %.3e):" % (label, gmax))
         for e, n, rn in rows[:6]:
             print("      %-50s err %.3e  |ref| %.3e" % (n, e, rn))
-        failures += [(label, n, e) for e, n, rn in rows if e > 0.2]
+        failures += [(label, n, e) for e, n, rn in rows if e > 0.1]
     assert not failures, failures[:10]
 
 
 def test_train_iteration_losses_and_grads_vs_golden():
     """One generator step and one discriminator step through the hand-written backward (TF32 gradient
     GEMMs) against the reference trainer's losses and gradients stored in the golden fixture.
-    Tolerances: losses 1e-2 relative; per-tensor gradient cosine similarity >= 0.98 on the stored strided
-    samples.  The hinge and L1 feature-matching losses are piecewise linear: a feature computed with an
+    Tolerances: losses 1e-2 relative (measured 5e-6); per-tensor gradient cosine similarity >= 0.998 on the stored
+    strided samples (measured >= 0.9991 for G, >= 0.9995 for D; round 1: 0.98).  The hinge and L1 feature-matching losses are piecewise linear: a feature computed with an
     11-bit significand flips sign(f_fake - f_real) for ~0.1 % of the elements, which alone moves the
     gradient by several % in relative L2, so an exact-arithmetic bound is checked separately with a smooth
     loss in test_backward_chain_smooth_loss_vs_oracle."""
@@ -385,7 +385,7 @@ def test_train_iteration_losses_and_grads_vs_golden():
             cos = _cosine(summary(p.grad, stride=101), z[k])
             print("   %-45s cosine %.4f  rel L2 %.3e" % (k, cos, _rel_l2(summary(p.grad, stride=101), z[k])))
             worst = min(worst, cos)
-    assert worst >= 0.98, worst
+    assert worst >= 0.998, worst
     assert named["backgroud_enc.layer4.conv.weight"].grad is None
     opt_G.step()
 
@@ -408,7 +408,7 @@ def test_train_iteration_losses_and_grads_vs_golden():
             cos = _cosine(summary(namedD[k[len("d0_grad/"):]].grad, stride=53), z[k])
             print("   %-45s cosine %.4f" % (k, cos))
             worst = min(worst, cos)
-    assert worst >= 0.98, worst
+    assert worst >= 0.998, worst
     opt_D.step()
 
 
