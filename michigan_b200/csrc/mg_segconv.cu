@@ -35,6 +35,7 @@ struct SegParams {
     int N, OH, OW, R;
     int tiles_w, tiles_h, num_tiles;
     uint32_t idesc;
+    int tma_store;   // 16-bit outputs leave through smem staging + TMA stores (out == null)
     int prof, dbg;   // dbg (MG_DBG bits, timing only): 1 no global stores, 2 no smem transposition
 };
 
@@ -44,7 +45,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 __global__ void __launch_bounds__(kSegThreads, 1)
-seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
+seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmHi,
+                  const __grid_constant__ CUtensorMap tmLo, const SegParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* w_s = smem;                                    // resident weights
@@ -56,7 +58,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
     uint64_t* t_empty = bars + 6;     // [2] 256 epilogue threads
     uint64_t* w_full = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    float* scratch = reinterpret_cast<float*>(smem + 3 * kSegTileBytes + 128);
+    float* scratch = reinterpret_cast<float*>(smem + 3 * kSegTileBytes + 1024);   // 1024-aligned: also the TMA-store staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -187,6 +189,59 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             tc_fence_before();
             mbar_arrive(&t_empty[s]);            // accumulator is in registers: release it before the stores
             if (prof) { const long long t1 = clock64(); c_ld += t1 - t0; t0 = t1; }
+            if (p.tma_store) {
+                // 16-bit outputs only: lane = pixel row of a [32 px][64 ch] box (two image rows of the tile).  Each lane lays its
+                // 128-byte row down in the SWIZZLE_128B pattern (16-byte chunk c at c ^ (row & 7): conflict-free per 8 lanes) and
+                // one lane hands the 4 KB box to the TMA unit, which writes whole lines and clips the part outside the image.
+                uint8_t* st_hi = reinterpret_cast<uint8_t*>(scratch) + ew * 8192;
+                uint8_t* st_lo = st_hi + 4096;
+                if (it > 0) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }
+                const float* bsrc = p.bias + half * 64;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* v = (c >> 1) == 0 ? v0 : (c >> 1) == 1 ? v1 : (c >> 1) == 2 ? v2 : v3;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bsrc + c * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bsrc + c * 8 + 4));
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        y[i] = __uint_as_float(v[(c & 1) * 8 + i]) + bb[i];
+                        if (p.act == 1) y[i] = fmaxf(y[i], 0.f);
+                        else if (p.act == 2) y[i] = y[i] > 0.f ? y[i] : 0.2f * y[i];
+                        if (p.round_out) y[i] = round_tf32(y[i]);
+                    }
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a = y[2 * i], b = y[2 * i + 1];
+                        if (p.out16_fmt == 1) {
+                            const __half2 h2 = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+                            h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                        } else {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                            const float2 hf = __bfloat1622float2(h2);
+                            h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            l[i] = pack_bf16x2(a - hf.x, b - hf.y);
+                        }
+                    }
+                    const int off = lane * 128 + ((c ^ (lane & 7)) << 4);
+                    *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                    if (p.out_lo) *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(MG_DBGV(p) & 1)) {
+                    tma_store_4d(&tmHi, st_hi, half * 64, ow0, oh0 + quarter * 2, n);
+                    if (p.out_lo) tma_store_4d(&tmLo, st_lo, half * 64, ow0, oh0 + quarter * 2, n);
+                    tma_store_commit();
+                }
+                if (prof) c_rest += clock64() - t0;
+                continue;
+            }
             // All 64 columns of this warp go through the scratch at once so that every global store request is a full
             // 128-byte line (the SM->L2 write path moves about one request per 11 cycles whatever its size: 32/64-byte
             // pieces made this kernel store-bound).  8 lanes serve one pixel: with a 16-bit output each lane owns 8
@@ -264,6 +319,7 @@ seg_mlp_tc_kernel(const __grid_constant__ CUtensorMap tmW, const SegParams p) {
             }
             if (prof) c_rest += clock64() - t0;
         }
+        if (p.tma_store && lane == 0) tma_store_wait_all();
         if (prof) {
             g_seg_prof[7] = (unsigned long long)(clock64() - t_begin); g_seg_prof[8] = (unsigned long long)c_wait;
             g_seg_prof[9] = (unsigned long long)c_ld; g_seg_prof[10] = (unsigned long long)c_rest;
@@ -339,7 +395,20 @@ extern "C" int mg_conv_seg_tc(const mg_thin_args* a, void* stream_) {
         int rc = encode_tensor_map(&tmW, (void*)a->w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    const size_t smem_bytes = 1024 + 3 * kSegTileBytes + 128 + 8 * 32 * 68 * 4;
+    CUtensorMap tmHi = tmW, tmLo = tmW;
+    p.tma_store = (tune(TK_SEG_TMA) && !a->out && a->out_hi) ? 1 : 0;
+    if (p.tma_store) {
+        // [N][OH][OW][128] 16-bit, box = 64 channels x 16 x 2 pixels = one epilogue warp's share of a tile
+        cuuint64_t dims[4] = {128, (cuuint64_t)a->OW, (cuuint64_t)a->OH, (cuuint64_t)a->N};
+        cuuint64_t strides[3] = {128 * 2, (cuuint64_t)a->OW * 256, (cuuint64_t)a->OW * a->OH * 256};
+        cuuint32_t box[4] = {64, 16, 2, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        const CUtensorMapDataType dt = a->out16_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        int rc = encode_tensor_map(&tmHi, a->out_hi, dt, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!rc && a->out_lo) rc = encode_tensor_map(&tmLo, a->out_lo, dt, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const size_t smem_bytes = 1024 + 3 * kSegTileBytes + 1024 + 8 * 32 * 68 * 4;
     static thread_local int attr_dev = -1;
     int dev = 0; cudaGetDevice(&dev);
     if (attr_dev != dev) {
@@ -349,6 +418,6 @@ extern "C" int mg_conv_seg_tc(const mg_thin_args* a, void* stream_) {
     }
     int grid = num_sms();
     if (grid > p.num_tiles) grid = p.num_tiles;
-    seg_mlp_tc_kernel<<<grid, kSegThreads, smem_bytes, stream>>>(tmW, p);
+    seg_mlp_tc_kernel<<<grid, kSegThreads, smem_bytes, stream>>>(tmW, tmHi, tmLo, p);
     return check_launch("mg_conv_seg_tc");
 }

@@ -33,6 +33,9 @@ struct WgradParams {
     int f16;                   // 0: fp32 storage read as TF32 (32 channels per 128 B row, K = 8 pixels per MMA);
                                // 2: bf16 operands (64 channels per row, K = 16 pixels per MMA)
     int kelem, mboxes, kmma;   // channels per box, boxes per 128-row M tile, pixels per MMA
+    int halo;                  // bf16, stride 1, KW >= 2: ONE input patch [(TW + KW - 1) x TH pixels] per stage instead of KW shifted
+                               // tiles; tap kw reads it through an operand descriptor that starts kw pixel rows (128 B) later
+    int xbox_bytes, x_tx_bytes;// smem slot of one input box (= box_bytes unless halo) and the bytes TMA writes into it
     uint32_t idesc, tmem_cols;
     float* dw;  // [Cout][KH*KW*Cin]
 };
@@ -71,8 +74,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // input tiles (accumulators kw*BN.. in TMEM), so dY is streamed KH (not KH*KW) times from HBM/L2.
     const int kBoxBytes = p.box_bytes;
     const int a_bytes = p.mboxes * kBoxBytes;           // M = 128 -> 4 boxes of 32 fp32 channels / 2 boxes of 64 bf16 channels
-    const int b1_bytes = (p.BN / p.kelem) * kBoxBytes;  // one tap's input tile
-    const int stage_bytes = a_bytes + p.KW * b1_bytes;
+    const int b1_bytes = (p.BN / p.kelem) * p.xbox_bytes;  // one tap's input tile (halo: the shared patch)
+    const int stage_bytes = a_bytes + (p.halo ? 1 : p.KW) * b1_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgStagesMax;
@@ -80,9 +83,11 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStagesMax + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // unit decode: blockIdx.x = ((kh * m_tiles + mt) * n_tiles + nt) * splits + split
-    int u = blockIdx.x;
-    const int split = u % p.splits; u /= p.splits;
+    // unit decode: blockIdx.x = split * units + (kh * m_tiles + mt) * n_tiles + nt
+    // units are the FAST index: the CTAs of one wave work on the same pixel range, so dY / X come from DRAM once per wave
+    const int n_units = p.KH * p.m_tiles * p.n_tiles;
+    int u = blockIdx.x % n_units;
+    const int split = blockIdx.x / n_units;
     const int nt = u % p.n_tiles; u /= p.n_tiles;
     const int mt = u % p.m_tiles;
     const int kh = u / p.m_tiles;
@@ -107,9 +112,10 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         // boxes: one 128 B swizzle row = 32 fp32), up to 16 bulk-tensor instructions.  Issued by one thread they cost more than
         // the stage's MMAs; here lane j issues box j, so a stage goes out in one pass.
         int st = 0; uint32_t ph = 0;
-        const uint32_t tx = (uint32_t)stage_bytes;
         const int nb_x = p.BN / p.kelem;
-        const int n_boxes = p.mboxes + p.KW * nb_x;
+        // bytes the TMA unit delivers per stage (a halo patch box may be shorter than its atom-aligned slot)
+        const uint32_t tx = (uint32_t)(a_bytes + (p.halo ? nb_x * p.x_tx_bytes : p.KW * b1_bytes));
+        const int n_boxes = p.mboxes + (p.halo ? 1 : p.KW) * nb_x;
         for (int t = t_begin; t < t_end; ++t) {
             const int tw = t % p.tiles_w;
             const int th = (t / p.tiles_w) % p.tiles_h;
@@ -126,7 +132,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     tma_load_4d(sa + b * kBoxBytes, &tmDY, &full_bar[st], mt * 128 + b * p.kelem, ow0, oh0, n0);
                 } else {
                     const int kw = (b - p.mboxes) / nb_x, j = (b - p.mboxes) - kw * nb_x;
-                    tma_load_4d(sa + a_bytes + kw * b1_bytes + j * kBoxBytes, &tmX, &full_bar[st], nt * p.BN + j * p.kelem,
+                    tma_load_4d(sa + a_bytes + kw * b1_bytes + j * p.xbox_bytes, &tmX, &full_bar[st], nt * p.BN + j * p.kelem,
                                 ow0 * p.stride - p.pad + kw, oh0 * p.stride - p.pad + kh, n0);
                 }
             }
@@ -145,7 +151,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                 for (int kw = issuer; kw < p.KW; kw += p.issuers)
                     for (int k = 0; k < p.pix_tile / p.kmma; ++k) {
                         const uint32_t koff = (uint32_t)(k * p.kmma * 128);      // kmma pixel rows of 128 B
-                        if (p.f16) {
+                        if (p.halo) {
+                            // K step k = tile row k (TW = 16 pixels = two contiguous 8-row swizzle groups); the input row starts
+                            // kw pixels into row k of the (TW + KW - 1)-wide patch
+                            const uint64_t da = umma_desc_mnmajor_sw128_16(sa + koff, kBoxBytes);
+                            const uint64_t db = umma_desc_mnmajor_sw128_16(sa + a_bytes + (uint32_t)((k * (p.TW + p.KW - 1) + kw) * 128), p.xbox_bytes);
+                            umma_f16(tmem_base + (uint32_t)(kw * p.BN), da, db, p.idesc, (first && k == 0) ? 0u : 1u);
+                        } else if (p.f16) {
                             const uint64_t da = umma_desc_mnmajor_sw128_16(sa + koff, kBoxBytes);
                             const uint64_t db = umma_desc_mnmajor_sw128_16(sa + a_bytes + kw * b1_bytes + koff, kBoxBytes);
                             umma_f16(tmem_base + (uint32_t)(kw * p.BN), da, db, p.idesc, (first && k == 0) ? 0u : 1u);
@@ -219,8 +231,11 @@ static int wgrad_launch(const void* dy, const void* x, float* dw, int N, int H, 
     // K (pixels) per stage: 64 when at least 3 stages fit in shared memory, else 32
     int pix_tile = 64;
     if ((200 * 1024) / ((p.mboxes + KW * (BN / kelem)) * 64 * 128) < 3) pix_tile = 32;
+    // halo schedule: tile 16 x 4 pixels (one K = 16 MMA per tile row), input patch (16 + KW - 1) x 4 pixels
+    p.halo = (fmt == 2 && stride == 1 && KW >= 2 && KW <= 4 && OW >= 16 && OH >= 4 && tune(TK_WGRAD_HALO)) ? 1 : 0;
+    if (p.halo) pix_tile = 64;
     p.pix_tile = pix_tile; p.box_bytes = pix_tile * 128;
-    p.TW = np2(OW) < 8 ? np2(OW) : 8;
+    p.TW = p.halo ? 16 : (np2(OW) < 8 ? np2(OW) : 8);
     int th = pix_tile / p.TW;
     p.TH = np2(OH) < th ? np2(OH) : th;
     p.TN = pix_tile / (p.TW * p.TH);
@@ -237,7 +252,10 @@ static int wgrad_launch(const void* dy, const void* x, float* dw, int N, int H, 
     if (splits < 1) splits = 1;
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     p.splits = splits;
-    const int stage_bytes = (p.mboxes + KW * (BN / kelem)) * p.box_bytes;
+    // halo: the patch box is rounded up to whole 1024 B swizzle atoms so that every box starts on an atom boundary
+    p.x_tx_bytes = p.halo ? (p.TW + KW - 1) * p.TH * p.TN * 128 : p.box_bytes;
+    p.xbox_bytes = (p.x_tx_bytes + 1023) / 1024 * 1024;
+    const int stage_bytes = p.mboxes * p.box_bytes + (p.halo ? 1 : KW) * (BN / kelem) * p.xbox_bytes;
     int stages = (200 * 1024) / stage_bytes;
     if (stages < 1) return set_error(-4, "mg_conv_wgrad: stage of %d bytes does not fit shared memory", stage_bytes);
     if (stages > kWgStagesMax) stages = kWgStagesMax;
@@ -262,7 +280,7 @@ static int wgrad_launch(const void* dy, const void* x, float* dw, int N, int H, 
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * esz, (cuuint64_t)W * Cin * esz, (cuuint64_t)H * W * Cin * esz};
-        cuuint32_t box[4] = {(cuuint32_t)kelem, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
+        cuuint32_t box[4] = {(cuuint32_t)kelem, (cuuint32_t)(p.halo ? p.TW + KW - 1 : p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TN};
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         int rc = encode_tensor_map(&tmX, (void*)x, dt, 4, dims, strides, box, es, sw);
         if (rc) return rc;

@@ -166,7 +166,7 @@ def test_fused_spade_epilogue(gen, N, h, C, xs):
     assert rel_err(nchw(got), ref) <= 3e-5
 
 
-@pytest.mark.parametrize("N,H,W,R,cin", [(2, 32, 32, 1, 4), (1, 64, 64, 4, 4), (3, 16, 16, 2, 4), (2, 24, 40, 1, 3)])
+@pytest.mark.parametrize("N,H,W,R,cin", [(2, 32, 32, 1, 4), (1, 64, 64, 4, 4), (3, 16, 16, 2, 4), (2, 24, 40, 1, 3), (2, 18, 9, 4, 4)])
 def test_seg_conv_tensor_core(gen, N, H, W, R, cin):
     """SPADE mlp_shared (normalization.py:92-96,110-111) as one K=128 bf16-split GEMM vs fp32 conv: 3e-5; the direct
     fp32 kernel (MG_SEG_TC=0 route) must agree as well."""
@@ -183,6 +183,25 @@ def test_seg_conv_tensor_core(gen, N, H, W, R, cin):
     assert rel_err(nchw(direct), ref) <= 2e-5
     o32, hi, _ = ops.conv_seg_tc(nhwc(seg), ops.pack_weight_seg_tc(w), b, seg_resize=R if R > 1 else 0, out_hw=(H, W), out16=(ops.F16, False))
     assert torch.equal(hi.float(), o32.half().float())
+    # 16-bit-only outputs leave through smem staging + TMA stores (MG_SEG_TMA=1, the default): bit-identical to the
+    # register-store epilogue for both formats, on ragged tiles too (the TMA unit clips the part outside the image)
+    from michigan_b200 import _lib
+    for fmt, split in ((ops.F16, False), (ops.BF16, True)):
+        outs = []
+        for knob in (0, 1):
+            prev = _lib.set_tuning("MG_SEG_TMA", knob)
+            try:
+                _, h16, l16 = ops.conv_seg_tc(nhwc(seg), ops.pack_weight_seg_tc(w), b, seg_resize=R if R > 1 else 0, out_hw=(H, W),
+                                              out16=(fmt, split), want_f32=False)
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_tuning("MG_SEG_TMA", prev)
+            outs.append((h16, l16))
+        assert torch.equal(outs[0][0], outs[1][0])
+        if split:
+            assert torch.equal(outs[0][1], outs[1][1])
+        recon = outs[1][0].float() + (outs[1][1].float() if split else 0)
+        assert rel_err(nchw(recon), ref) <= (3e-5 if split else 1e-3)
 
 
 @pytest.mark.parametrize("Cin,CinP,Cout,k,s,p,pm", [(4, 4, 128, 3, 1, 1, 0), (7, 8, 64, 4, 2, 2, 0), (3, 4, 64, 7, 1, 3, 1), (3, 4, 64, 3, 2, 1, 0)])
@@ -236,7 +255,8 @@ def test_tensor_core_wgrad_and_dgrad(gen, N, h, Cin, Cout, k, s, p):
     assert rel_err(nchw(dx), x.grad) <= 5e-5
 
 
-@pytest.mark.parametrize("N,h,Cin,Cout,k,s,p", [(2, 32, 64, 64, 3, 1, 1), (2, 40, 128, 256, 3, 1, 1), (2, 33, 64, 128, 4, 2, 2), (3, 8, 128, 64, 1, 1, 0)])
+@pytest.mark.parametrize("N,h,Cin,Cout,k,s,p", [(2, 32, 64, 64, 3, 1, 1), (2, 40, 128, 256, 3, 1, 1), (2, 33, 64, 128, 4, 2, 2), (3, 8, 128, 64, 1, 1, 0),
+                                                   (2, 33, 256, 128, 4, 1, 2), (1, 20, 64, 64, 3, 1, 1)])
 def test_wgrad_bf16_operands(gen, N, h, Cin, Cout, k, s, p):
     """The weight-gradient GEMM with bf16 operands (MN-major, plain 128B swizzle, K = 16 pixels per MMA) against torch autograd on
     bf16-exact operands (fp32 accumulation on both sides)."""
@@ -246,9 +266,15 @@ def test_wgrad_bf16_operands(gen, N, h, Cin, Cout, k, s, p):
     y = F.conv2d(x, w, None, stride=s, padding=p)
     dy = torch.randn(y.shape, generator=gen).to(dev).bfloat16().float()
     y.backward(dy)
-    dwp = ops.conv_wgrad16(nhwc(dy).bfloat16(), nhwc(x.detach()).bfloat16(), k, k, s, p)
-    dw = ops.unpack_wgrad(dwp, tuple(w.shape))
-    assert rel_err(dw, w.grad) <= 5e-5
+    from michigan_b200 import _lib
+    for halo in (0, 1):      # 1 (default): stride-1 layers load ONE input patch per stage, the KW taps read shifted views of it
+        prev = _lib.set_tuning("MG_WGRAD_HALO", halo)
+        try:
+            dwp = ops.conv_wgrad16(nhwc(dy).bfloat16(), nhwc(x.detach()).bfloat16(), k, k, s, p)
+            dw = ops.unpack_wgrad(dwp, tuple(w.shape))
+        finally:
+            _lib.set_tuning("MG_WGRAD_HALO", prev)
+        assert rel_err(dw, w.grad) <= 5e-5, halo
     assert torch.equal(ops.cvt16(nhwc(dy)), nhwc(dy).bfloat16())
     sums, d16 = ops.chan_sum_cvt16(nhwc(dy))
     assert torch.equal(d16, nhwc(dy).bfloat16())

@@ -26,7 +26,8 @@ elif which in ("wgrad16", "wgrad32"):   # gamma|beta weight gradient of up_3
 elif which == "seg":          # SPADE mlp_shared 4 -> 128 at 512x512, fp16 output
     seg, w, b = r(N, S, S, 4), r(128, 4, 3, 3) / 6, torch.zeros(128, device=dev)
     wp = ops.pack_mlp_shared(w)
-    f = lambda: ops.mlp_shared(seg, wp, b, seg_resize=1, out_hw=(S, S), out16=(ops.F16, False), want_f32=False)
+    o16 = (ops.BF16, True) if os.environ.get("MG_SEG_SPLIT") else (ops.F16, False)
+    f = lambda: ops.mlp_shared(seg, wp, b, seg_resize=1, out_hw=(S, S), out16=o16, want_f32=False)
 elif which == "stats":        # BN statistics of [8,512,512,64]
     x = r(N, S, S, 64)
     f = lambda: ops.bn_sums(x)
@@ -42,4 +43,12 @@ else:
 for _ in range(4):
     f()
 torch.cuda.synchronize()
+if os.environ.get("MG_TIME"):          # not under ncu: average of 20 launches, CUDA events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    print("%s: %.4f ms/launch" % (which, e0.elapsed_time(e1) / 20))
 print("done", which)
