@@ -48,7 +48,7 @@ struct IgemmParams {
     const float* gbias1;
     const float* bbias;
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
-    int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default); scratch offset in smem
+    int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default), 2 = SPADE row-per-lane + TMA stores; scratch offset in smem
     // halo mode (3x3, stride 1, pad 1): one [PW x (TH+2)] input patch per K chunk serves all 9 taps
     int halo, PW, patch_bytes, patch_tx, a_slots, b_slots, b_slot_bytes, acc_cols, merged, n_items, bar_off;
     uint32_t idesc2;
@@ -273,6 +273,93 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
                 if (has_lo) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + eo) = make_uint2(lo[0], lo[1]);
             }
         }
+    }
+}
+
+// SPADE -> bf16 hi/lo operand, row-per-lane + TMA stores (IgemmParams::epi_impl == 2; SPEC 1 LeakyReLU, SPEC 2 no activation).
+// Preconditions (checked by the launcher): BN = 256 (gamma | beta halves of 128 columns, this warp owns 64 output channels),
+// tile 16 x 8 pixels of ONE image, plain output layout, no merged split.  The lane keeps its TMEM row = pixel; the 16-bit
+// results of a 32-channel group are laid down as [32 pixels][64 B] in the SWIZZLE_64B pattern (16-byte chunk c of row r at
+// c ^ ((r >> 1) & 3): conflict-free per 8 lanes) and one lane hands the two 2 KB boxes (hi, lo) to the TMA unit, which
+// writes whole sectors and clips what lies outside the image.  Against the transposed epilogue this drops the smem
+// transposition and every 8-byte global store (the SM -> L2 path moves ~1 request per 11 cycles whatever its size);
+// x is read row-per-lane (with the fused 2x upsampling only 8 distinct pixels per warp instruction).
+// `stage`: this warp's 4 KB staging buffer (512 B aligned); `pending`: a TMA store of this warp may still be reading it.
+template <int SPEC>
+__device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, uint8_t* stage, const CUtensorMap* tmHi, const CUtensorMap* tmLo,
+                                                        uint64_t* tfull, uint32_t parity, uint32_t t_acc, int nt, int tw, int th, int tn,
+                                                        int quarter, int half, int lane, bool& pending, long long* w_tfull) {
+    constexpr int act = SPEC == 1 ? 2 : 0;
+    const int ch_tile = p.BN >> 1;                      // 128
+    const int ow = tw * 16 + (lane & 15), oh = th * 8 + quarter * 2 + (lane >> 4);
+    const bool valid = ow < p.OW && oh < p.OH;
+    const float* xrow = p.x + ((size_t)((size_t)tn * p.XH + (oh >> p.x_shift)) * p.XW + (ow >> p.x_shift)) * p.Cout;
+    uint8_t* st_hi = stage;
+    uint8_t* st_lo = stage + 2048;
+    const int sw = (lane >> 1) & 3;
+    const long long t0 = w_tfull ? clock64() : 0;
+    mbar_wait(tfull, parity);
+    if (w_tfull) *w_tfull += clock64() - t0;
+    tc_fence_after();
+    const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+        if (MG_DBGV(p) & 4) break;
+        const int col = half * 64 + g * 32;              // gamma column of this group inside the tile; beta at + ch_tile
+        const int cch = nt * ch_tile + col;              // output channel
+        uint32_t g0[16], g1[16], b0[16], b1[16];
+        tmem_ld16(t_row + (uint32_t)col, g0);
+        tmem_ld16(t_row + (uint32_t)(col + 16), g1);
+        tmem_ld16(t_row + (uint32_t)(col + ch_tile), b0);
+        tmem_ld16(t_row + (uint32_t)(col + ch_tile + 16), b1);
+        float4 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            xv[i] = valid ? __ldg(reinterpret_cast<const float4*>(xrow + cch + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tmem_ld_wait();
+        if (pending) { if (lane == 0) tma_store_wait_read(); __syncwarp(); pending = false; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                    // 16-byte chunk = 8 channels
+            const uint32_t* gv = c < 2 ? g0 : g1;
+            const uint32_t* bv = c < 2 ? b0 : b1;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int e = (c & 1) * 8 + h2 * 4;      // element inside the 16-column register array
+                const int ch = cch + c * 8 + h2 * 4;
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.nscale + ch));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(p.nshift + ch));
+                const float4 g1b = __ldg(reinterpret_cast<const float4*>(p.gbias1 + ch));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bbias + ch));
+                const float4 x4 = xv[c * 2 + h2];
+                float y[4];
+                y[0] = fmaf(x4.x, sc.x, sh.x) * (g1b.x + __uint_as_float(gv[e])) + (bb.x + __uint_as_float(bv[e]));
+                y[1] = fmaf(x4.y, sc.y, sh.y) * (g1b.y + __uint_as_float(gv[e + 1])) + (bb.y + __uint_as_float(bv[e + 1]));
+                y[2] = fmaf(x4.z, sc.z, sh.z) * (g1b.z + __uint_as_float(gv[e + 2])) + (bb.z + __uint_as_float(bv[e + 2]));
+                y[3] = fmaf(x4.w, sc.w, sh.w) * (g1b.w + __uint_as_float(gv[e + 3])) + (bb.w + __uint_as_float(bv[e + 3]));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] = apply_act(y[i], act);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+                    const float2 hf = __bfloat1622float2(hh);
+                    const __nv_bfloat162 ll = __floats2bfloat162_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
+                    hi[h2 * 2 + i] = *reinterpret_cast<const uint32_t*>(&hh);
+                    lo[h2 * 2 + i] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+            }
+            const int off = lane * 64 + ((c ^ sw) << 4);
+            *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(MG_DBGV(p) & (8 | 32))) {
+            tma_store_4d(tmHi, st_hi, cch, tw * 16, th * 8 + quarter * 2, tn);
+            tma_store_4d(tmLo, st_lo, cch, tw * 16, th * 8 + quarter * 2, tn);
+            tma_store_commit();
+        }
+        pending = true;
     }
 }
 

@@ -67,7 +67,8 @@ __device__ __forceinline__ void store16(const IgemmParams& p, const float (&y)[1
 template <int SPEC, int CW>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOHi,
+                  const __grid_constant__ CUtensorMap tmOLo, const IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align the operand ring (SWIZZLE_128B atoms are 1024 B).
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -352,6 +353,40 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             g_igemm_prof[o] = (unsigned long long)total; g_igemm_prof[o + 1] = (unsigned long long)w_tfull;
             g_igemm_prof[o + 2] = (unsigned long long)(total - w_tfull); g_igemm_prof[o + 3] = (unsigned long long)ntile;
         }
+    } else if (warp >= 2 && warp < 2 + kNumEpiWarps && p.epi_impl == 2) {
+        // ===================== epilogue warps: SPADE -> bf16 hi/lo, row-per-lane + TMA stores (mg_epilogue.cuh) ===============
+        if constexpr (SPEC == 1 || SPEC == 2) {
+            const int ew = warp - 2;
+            const int quarter = warp & 3;
+            const int half = ew >> 2;
+            uint8_t* stage = smem + p.epi_off + ew * 4096;
+            int acc = 0;
+            uint32_t aph = 0;
+            bool pending = false;
+            const bool prof = (MG_DBGV(p) & 16) && blockIdx.x == 0 && (ew == 0 || ew == 7) && lane == 0;
+            long long w_tfull = 0, t_begin = prof ? clock64() : 0;
+            int ntile = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int m = tile / p.n_tiles;
+                const int tw = m % p.tiles_w;
+                const int th = (m / p.tiles_w) % p.tiles_h;
+                const int tn = m / m_tiles_per_img;
+                epilogue_tile_spade_tma<SPEC>(p, stage, &tmOHi, &tmOLo, &tfull_bar[acc], aph, tmem_base + (uint32_t)(acc * p.acc_cols), nt, tw,
+                                              th, tn, quarter, half, lane, pending, prof ? &w_tfull : nullptr);
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                ++ntile;
+                if (++acc == 2) { acc = 0; aph ^= 1; }
+            }
+            if (lane == 0) tma_store_wait_all();
+            if (prof) {
+                const int o = ew == 0 ? 5 : 9;
+                const long long total = clock64() - t_begin;
+                g_igemm_prof[o] = (unsigned long long)total; g_igemm_prof[o + 1] = (unsigned long long)w_tfull;
+                g_igemm_prof[o + 2] = (unsigned long long)(total - w_tfull); g_igemm_prof[o + 3] = (unsigned long long)ntile;
+            }
+        }
     } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
         // ===================== epilogue warps (row-per-lane reference implementation) =====================
         const int ew = warp - 2;
@@ -559,7 +594,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     const int cw_spade = tune(TK_CW_SPADE);
     int cw = (span_epi % 32 == 0 && !p.epi_cw16) ? 32 : 16;
     if (a->epi == MG_EPI_SPADE) cw = (cw_spade == 32 && span_epi % 32 == 0) ? 32 : 16;
-    const int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * (cw + 4) * 4 : 0;
+    int scratch_bytes = p.epi_impl == 1 ? kNumEpiWarps * 32 * (cw + 4) * 4 : 0;
     // Halo mode: 3x3 / stride 1 / pad 1 convolutions (the SPADE gamma|beta GEMMs, conv_0/conv_1 and their dgrads) load
     // one [PW x (TH+2)] input patch per K chunk and read the 9 taps out of it through shifted UMMA descriptors.
     // MG_HALO: 0 off (default: measured no faster on B200 - these kernels are bound by the MMA operand fetch / epilogue,
@@ -598,6 +633,14 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.a_fmt = a->a_fmt; p.parts = merged ? 2 : (a->split ? 3 : 1); p.kelem = kelem;
     p.out_hi = a->out_hi; p.out_lo = a->out_lo; p.out16_fmt = a->out16_fmt;
     p.acc_cols = p.merged ? 2 * BN : BN;
+    // SPADE -> bf16 hi/lo operand at BN = 256 (the dominant GEMMs of the forward): row-per-lane epilogue that leaves through
+    // smem staging + TMA stores (epilogue_tile_spade_tma); 32 KB of staging instead of 20 KB of transposition scratch still
+    // leaves room for the 4-stage ring.  MG_EPI_TMA=0 keeps the transposed epilogue.
+    const bool tma_epi = tune(TK_EPI_TMA) && p.epi_impl == 1 && a->epi == MG_EPI_SPADE && !a->out && a->out_hi && a->out_lo &&
+                         a->out16_fmt == 2 && !a->aux_out && !a->round_out && (a->act == MG_ACT_LRELU || a->act == MG_ACT_NONE) && !merged &&
+                         !halo && BN == 256 && a->Cout % 32 == 0 && p.TW == 16 && p.TH == 8 && p.TN == 1 && p.os == 1 &&
+                         p.OHF == a->OH && p.OWF == a->OW && tune(TK_GROUP3) < 2;
+    if (tma_epi) { p.epi_impl = 2; scratch_bytes = kNumEpiWarps * 4096; }
 #ifdef MG_PROBES
     p.dbg = probe_bits();
 #endif
@@ -656,7 +699,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     p.nscale = a->nscale; p.nshift = a->nshift; p.gbias1 = a->gbias1; p.bbias = a->bbias; p.aux = a->aux_out;
 
     int spec = 0;
-    if (p.epi_impl == 1 && a->epi == MG_EPI_SPADE && !a->out && a->out_hi && a->out_lo && a->out16_fmt == 2 && !a->aux_out &&
+    if (p.epi_impl >= 1 && a->epi == MG_EPI_SPADE && !a->out && a->out_hi && a->out_lo && a->out16_fmt == 2 && !a->aux_out &&
         !a->round_out && (a->act == MG_ACT_LRELU || a->act == MG_ACT_NONE))
         spec = a->act == MG_ACT_LRELU ? 1 : 2;
     // 3x3 / stride 1 / pad 1 layers: the halo-patch + M-tile-group kernel (mg_conv3x3.cu) moves 3-5x fewer bytes through L2.
@@ -697,6 +740,17 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         if (rc) return rc;
     }
 
+    CUtensorMap tmOHi = tmA, tmOLo = tmA;
+    if (p.epi_impl == 2) {
+        // [N][OH][OW][Cout] bf16; box = 32 channels x 16 x 2 pixels (one epilogue warp's quarter of a tile, 64-byte rows)
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)a->OW, (cuuint64_t)a->OH, (cuuint64_t)a->N};
+        cuuint64_t strides[3] = {(cuuint64_t)a->Cout * 2, (cuuint64_t)a->OW * a->Cout * 2, (cuuint64_t)a->OH * a->OW * a->Cout * 2};
+        cuuint32_t box[4] = {32, 16, 2, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        int rc = encode_tensor_map(&tmOHi, a->out_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (!rc) rc = encode_tensor_map(&tmOLo, a->out_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
     const size_t smem_bytes = ring_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + scratch_bytes;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
@@ -713,7 +767,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (grid > p.num_tiles) grid = p.num_tiles;
-#define MG_LAUNCH(S, C) igemm_tf32_kernel<S, C><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p)
+#define MG_LAUNCH(S, C) igemm_tf32_kernel<S, C><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOHi, tmOLo, p)
     if (spec == 1) { if (cw == 32) MG_LAUNCH(1, 32); else MG_LAUNCH(1, 16); }
     else if (spec == 2) { if (cw == 32) MG_LAUNCH(2, 32); else MG_LAUNCH(2, 16); }
     else { if (cw == 32) MG_LAUNCH(0, 32); else MG_LAUNCH(0, 16); }

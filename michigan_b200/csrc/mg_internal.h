@@ -32,6 +32,7 @@ enum TuneKnob {
     TK_GROUP3,           // MG_GROUP3: 3x3/s1 convs on the halo-patch + M-tile-group kernel (mg_conv3x3.cu): 0 off, 1 thin N, 2 all
     TK_SEG_TMA,          // MG_SEG_TMA: 16-bit outputs of the seg conv through smem staging + TMA stores (default 1)
     TK_WGRAD_HALO,       // MG_WGRAD_HALO: bf16 stride-1 weight gradients load one input patch per stage for all KW taps (default 1)
+    TK_EPI_TMA,          // MG_EPI_TMA: SPADE -> bf16 hi/lo epilogue at BN 256 row-per-lane through smem staging + TMA stores (default 1)
     TK_COUNT
 };
 int tune(int knob);

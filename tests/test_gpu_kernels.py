@@ -439,6 +439,40 @@ def test_conv3x3_group_kernel_spade_epilogue(gen):
     assert rel_err(outs[2], outs[0]) <= 2e-5
 
 
+@pytest.mark.parametrize("N,h,w,C,xsh,act", [(2, 32, 32, 128, 1, 2), (1, 24, 40, 128, 0, 0), (2, 16, 48, 256, 1, 2)])
+def test_spade_epilogue_tma_store(gen, N, h, w, C, xsh, act):
+    """SPADE gamma|beta GEMM -> bf16 hi/lo operand at BN = 256: the row-per-lane epilogue that leaves through smem staging and
+    TMA stores (MG_EPI_TMA=1, default) against the transposed register-store epilogue (MG_EPI_TMA=0) and the fp32 formula;
+    ragged tiles (24 x 40) rely on the TMA unit clipping the box."""
+    ops = _ops()
+    actv = torch.randn(N, h, w, 128, generator=gen).to(dev)
+    wg = (torch.randn(C, 128, 3, 3, generator=gen) / 34).to(dev)
+    wb = (torch.randn(C, 128, 3, 3, generator=gen) / 34).to(dev)
+    xs = torch.randn(N, h >> xsh, w >> xsh, C, generator=gen).to(dev)
+    ns, nh, g1, bb = [torch.randn(C, generator=gen).to(dev) for _ in range(4)]
+    wp = ops.pack_weight_gb16(wg, wb)
+    outs = {}
+    for knob in (1, 0):
+        prev = _lib_mod().set_tuning("MG_EPI_TMA", knob)
+        try:
+            _, hi, lo = ops.conv_igemm(actv.half(), wp, C, 3, 3, 1, 1, act=act, a_fmt=ops.F16, spade=(xs, xsh, ns, nh, g1, bb),
+                                       out16=(ops.BF16, True), want_f32=False, max_ctas=3)
+            torch.cuda.synchronize()
+            outs[knob] = hi.float() + lo.float()
+        finally:
+            _lib_mod().set_tuning("MG_EPI_TMA", prev)
+    a16 = nchw(actv.half().float())
+    gamma = F.conv2d(a16, wg.half().float(), None, padding=1)
+    beta = F.conv2d(a16, wb.half().float(), None, padding=1)
+    xu = F.interpolate(nchw(xs), scale_factor=2, mode="nearest") if xsh else nchw(xs)
+    xh = xu * ns.view(1, -1, 1, 1) + nh.view(1, -1, 1, 1)
+    ref = xh * (g1.view(1, -1, 1, 1) + gamma) + (bb.view(1, -1, 1, 1) + beta)
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    assert rel_err(nchw(outs[1]), ref) <= 1e-4 and rel_err(nchw(outs[0]), ref) <= 1e-4
+    assert rel_err(outs[1], outs[0]) <= 2e-6
+
+
 def test_input_prologue_kernels_vs_reference_formulas(gen):
     """The GPU input prologue (noise pyramid, orientation RGB, hole mask) against numpy/cv2 restatements of the reference's
     per-sample CPU functions (data/base_dataset.py:335-396) on identical random draws."""
