@@ -495,7 +495,7 @@ conv_to1_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 // x viewed as [B][P][C]; sums [B][2][C] doubles.  Threads along channels (float4), rows of threads
 // stride over pixels; fp32 partials are flushed to double every 32 pixels; warp-free smem reduce,
 // one double atomic per (block, channel, moment).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __restrict__ sums, int blocks_per_b,
                   uint16_t* __restrict__ out16) {
     const int G = C / 4;                    // float4 groups
@@ -512,8 +512,7 @@ chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __res
         float fs[4] = {0, 0, 0, 0}, fq[4] = {0, 0, 0, 0};
         int cnt = 0;
         if (threadIdx.x < rows * tpr) {
-            for (long long pidx = (long long)blk * rows + tr; pidx < P; pidx += (long long)blocks_per_b * rows) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)pidx * C) + g0);
+            auto add = [&](const float4 v, long long pidx) {
                 if (out16) {   // bf16 copy in the same pass (operand of the 16-bit gradient GEMMs; B == 1 only)
                     const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), bb = __floats2bfloat162_rn(v.z, v.w);
                     *reinterpret_cast<uint2*>(out16 + (size_t)pidx * C + g0 * 4) =
@@ -527,7 +526,19 @@ chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __res
                     for (int i = 0; i < 4; ++i) { s[i] += fs[i]; q[i] += fq[i]; fs[i] = 0.f; fq[i] = 0.f; }
                     cnt = 0;
                 }
+            };
+            // four independent loads in flight per thread (one was 60 % of the HBM rate: 32 warps x 512 B per SM does not cover
+            // the DRAM latency); the accumulation order, and with it every bit of the result, is unchanged
+            const long long step = (long long)blocks_per_b * rows;
+            long long pidx = (long long)blk * rows + tr;
+            for (; pidx + 3 * step < P; pidx += 4 * step) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(pidx + u * step) * C) + g0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) add(v[u], pidx + u * step);
             }
+            for (; pidx < P; pidx += step) add(__ldg(reinterpret_cast<const float4*>(xb + (size_t)pidx * C) + g0), pidx);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { s[i] += fs[i]; q[i] += fq[i]; }
         }
@@ -1000,7 +1011,7 @@ static int launch_stats(const float* x, int B, long long P, int C, double* sums,
     const int tpr = G < 256 ? G : 256;
     const int rows = 256 / tpr;
     long long want = (P + (long long)rows * 8 - 1) / ((long long)rows * 8);
-    long long cap = ((long long)num_sms() * 4 + B - 1) / B;
+    long long cap = ((long long)num_sms() * 3 + B - 1) / B;   // 3 resident blocks per SM (80 registers): one wave
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     chan_stats_kernel<<<(int)want * B, 256, 0, st>>>(x, P, C, sums, (int)want, out16);

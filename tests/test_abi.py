@@ -78,3 +78,18 @@ def test_ops_refuse_cpu_tensors():
         ops.bn_sums(torch.zeros(1, 4, 4, 8))
     with pytest.raises(_lib.MichiganNativeError):
         ops.pack_weight(torch.zeros(32, 32, 3, 3))
+
+
+def test_schedule_knobs_named_in_the_header_exist():
+    """Every schedule knob the header documents is known to mg_get_tuning / mg_set_tuning (host-only calls); unknown names fail."""
+    import re
+    from michigan_b200 import _lib
+    lib = _lib.load()
+    text = open(os.path.join(ROOT, "include", "michigan_b200.h")).read()
+    names = sorted(set(re.findall(r'"(MG_[A-Z0-9_]+)"', text)))
+    assert {"MG_DUAL", "MG_GROUP3", "MG_SEG_TMA", "MG_WGRAD_HALO", "MG_EPI_TMA"} <= set(names)
+    for n in names:
+        v = lib.mg_get_tuning(n.encode())
+        assert v > -(1 << 30), n
+        assert lib.mg_set_tuning(n.encode(), v) == 0, n
+    assert lib.mg_set_tuning(b"MG_NO_SUCH_KNOB", 1) < 0

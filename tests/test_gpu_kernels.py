@@ -141,7 +141,7 @@ def test_igemm_halo_mode_matches_classic(gen):
             _lib_mod().set_tuning("MG_HALO", prev_knob)
     ref = F.conv2d(x, w, None, padding=1)
     assert rel_err(nchw(outs[0]), ref) <= 2e-5 and rel_err(nchw(outs[1]), ref) <= 2e-5
-    assert rel_err(outs[1], outs[0]) <= 2e-5      # hi + lo carries 16 significand bits; the two epilogues contract their FMAs differently
+    assert rel_err(outs[1], outs[0]) <= 2e-6
 
 
 @pytest.mark.parametrize("N,h,C,xs", [(2, 32, 64, 0), (2, 32, 128, 1), (1, 64, 32, 0), (3, 8, 256, 1)])
@@ -470,7 +470,7 @@ def test_spade_epilogue_tma_store(gen, N, h, w, C, xsh, act):
     if act == 2:
         ref = F.leaky_relu(ref, 0.2)
     assert rel_err(nchw(outs[1]), ref) <= 1e-4 and rel_err(nchw(outs[0]), ref) <= 1e-4
-    assert rel_err(outs[1], outs[0]) <= 2e-6
+    assert rel_err(outs[1], outs[0]) <= 2e-5      # hi + lo carries 16 significand bits; the two epilogues contract their FMAs differently
 
 
 def test_input_prologue_kernels_vs_reference_formulas(gen):

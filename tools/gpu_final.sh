@@ -16,3 +16,5 @@ print("train", t.get("ms_per_step"), t.get("value"), "e2e", t.get("e2e", {}).get
 print("clocks", d.get("clocks"), "cpu", d.get("cpu_baseline", {}).get("value"))
 PY
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref_n1.json 2>/dev/null; tail -c 400 gpurun_out/r02_bench_ref_n1.json
+MG_TIME=1 timeout 120 python tools/run_kernel.py stats 2>&1 | grep ms/launch
+if [ "$1" = "ncu" ]; then bash tools/ncu_kernels.sh spade seg wgrad16 stats; fi
