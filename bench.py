@@ -224,10 +224,11 @@ def run_reference_arm(a):
 
 # ================================================================================================ single-kernel rooflines
 # DRAM traffic of one launch of the dominant kernel from the `ncu --set full` capture committed under profiles/
-# (dram__bytes_read.sum + dram__bytes_write.sum at N=8); algorithmic bytes = actv fp16 268 MB + x fp32 268 MB + weights
-# 0.6 MB read, bf16 hi+lo 537 MB written.
-NCU_TRAFFIC_BYTES_N8 = 810.322432e6 + 1027.503e6
-NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_spade_gemm_f16.txt"
+# (dram__bytes_read.sum + dram__bytes_write.sum at N=8); algorithmic bytes at N=8 (2,097,152 pixels): actv fp16 128 ch 537 MB +
+# x fp32 128 ch at half resolution 268 MB + weights 0.6 MB read, bf16 hi+lo 128 ch 1074 MB written - the kernel moves its
+# algorithmic bytes and nothing more.
+NCU_TRAFFIC_BYTES_N8 = 809.607936e6 + 1027.305e6
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_spade_gemm_f16_tma.txt"
 
 
 def _time_kernel(f, reps=5):
