@@ -48,6 +48,7 @@ struct IgemmParams {
     const float* gbias1;
     const float* bbias;
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
+    int epi_xpf;                       // TMA SPADE epilogue: prefetch x ahead of the accumulator wait (MG_EPI_TMA=2)
     int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default), 2 = SPADE row-per-lane + TMA stores; scratch offset in smem
     // halo mode (3x3, stride 1, pad 1): one [PW x (TH+2)] input patch per K chunk serves all 9 taps
     int halo, PW, patch_bytes, patch_tx, a_slots, b_slots, b_slot_bytes, acc_cols, merged, n_items, bar_off;
@@ -297,6 +298,13 @@ __device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, ui
     uint8_t* st_hi = stage;
     uint8_t* st_lo = stage + 2048;
     const int sw = (lane >> 1) & 3;
+    const bool xok = valid && !(MG_DBGV(p) & 64);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // x does not depend on the accumulator: with epi_xpf the lane's 128-byte x line of the first 32-channel group is pulled into L1
+    // BEFORE waiting for the tile and the second group's while the first is computed - the real loads then hit L1 instead of
+    // paying an L2 / DRAM round trip on the epilogue's critical path (a prefetch costs no registers)
+    const float* xg0 = xrow + nt * ch_tile + half * 64;
+    if (p.epi_xpf && xok) asm volatile("prefetch.global.L1 [%0];" :: "l"(xg0));
     const long long t0 = w_tfull ? clock64() : 0;
     mbar_wait(tfull, parity);
     if (w_tfull) *w_tfull += clock64() - t0;
@@ -314,8 +322,8 @@ __device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, ui
         tmem_ld16(t_row + (uint32_t)(col + ch_tile + 16), b1);
         float4 xv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            xv[i] = valid ? __ldg(reinterpret_cast<const float4*>(xrow + cch + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) xv[i] = xok ? __ldg(reinterpret_cast<const float4*>(xrow + cch + 4 * i)) : zero4;
+        if (p.epi_xpf && xok && g == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(xg0 + 32));
         tmem_ld_wait();
         if (pending) { if (lane == 0) tma_store_wait_read(); __syncwarp(); pending = false; }
 #pragma unroll

@@ -568,6 +568,16 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
         BN = coutg >= 256 ? 256 : coutg;
         if (a->epi == MG_EPI_SPADE && BN < 64) BN = 64;
     }
+    if (a->BN == 0 && a->epi != MG_EPI_SPADE && tune(TK_BN_FILL)) {
+        // Under-filled grids (the 8x8 .. 32x32 layers: 1024 -> 1024 at 8x8 is 4 pixel tiles x 4 column tiles = 16 CTAs on 148
+        // SMs): halve BN while twice as many tiles still fit one wave.  Thinner tiles cost MMA efficiency, idle SMs cost more
+        // (head_0.conv_0: 198 us on 16 CTAs).  The weight operand layout does not depend on BN.
+        const int tw = next_pow2(a->OW) < 16 ? next_pow2(a->OW) : 16;
+        const int th = next_pow2(a->OH) < 128 / tw ? next_pow2(a->OH) : 128 / tw;
+        const int tn = 128 / (tw * th);
+        const long long m_tiles = (long long)((a->OW + tw - 1) / tw) * ((a->OH + th - 1) / th) * ((a->N + tn - 1) / tn);
+        while (BN > 64 && coutg % (BN / 2) == 0 && m_tiles * (coutg / BN) * 2 <= num_sms()) BN /= 2;
+    }
     if (BN % 32 != 0 || BN < 32 || BN > 256) return set_error(-3, "mg_conv_igemm: bad BN %d", BN);
     if (coutg % BN != 0) return set_error(-4, "mg_conv_igemm: GEMM N %d not a multiple of BN %d", coutg, BN);
     if (a->epi == MG_EPI_SPADE && (BN % 64 != 0 || !a->x || !a->nscale || !a->nshift || !a->gbias1 || !a->bbias))
@@ -640,7 +650,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
                          a->out16_fmt == 2 && !a->aux_out && !a->round_out && (a->act == MG_ACT_LRELU || a->act == MG_ACT_NONE) && !merged &&
                          !halo && BN == 256 && a->Cout % 32 == 0 && p.TW == 16 && p.TH == 8 && p.TN == 1 && p.os == 1 &&
                          p.OHF == a->OH && p.OWF == a->OW && tune(TK_GROUP3) < 2;
-    if (tma_epi) { p.epi_impl = 2; scratch_bytes = kNumEpiWarps * 4096; }
+    if (tma_epi) { p.epi_impl = 2; p.epi_xpf = tune(TK_EPI_TMA) >= 2 ? 1 : 0; scratch_bytes = kNumEpiWarps * 4096; }
 #ifdef MG_PROBES
     p.dbg = probe_bits();
 #endif

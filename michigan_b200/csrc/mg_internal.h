@@ -33,6 +33,7 @@ enum TuneKnob {
     TK_SEG_TMA,          // MG_SEG_TMA: 16-bit outputs of the seg conv through smem staging + TMA stores (default 1)
     TK_WGRAD_HALO,       // MG_WGRAD_HALO: bf16 stride-1 weight gradients load one input patch per stage for all KW taps (default 1)
     TK_EPI_TMA,          // MG_EPI_TMA: SPADE -> bf16 hi/lo epilogue at BN 256 row-per-lane through smem staging + TMA stores (default 1)
+    TK_BN_FILL,          // MG_BN_FILL: generic convs whose tiles do not fill the SMs use a narrower BN (default 1)
     TK_COUNT
 };
 int tune(int knob);

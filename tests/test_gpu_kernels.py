@@ -452,7 +452,7 @@ def test_spade_epilogue_tma_store(gen, N, h, w, C, xsh, act):
     ns, nh, g1, bb = [torch.randn(C, generator=gen).to(dev) for _ in range(4)]
     wp = ops.pack_weight_gb16(wg, wb)
     outs = {}
-    for knob in (1, 0):
+    for knob in (2, 1, 0):      # 2 = 1 + L1 prefetch of x ahead of the accumulator wait
         prev = _lib_mod().set_tuning("MG_EPI_TMA", knob)
         try:
             _, hi, lo = ops.conv_igemm(actv.half(), wp, C, 3, 3, 1, 1, act=act, a_fmt=ops.F16, spade=(xs, xsh, ns, nh, g1, bb),
@@ -470,6 +470,7 @@ def test_spade_epilogue_tma_store(gen, N, h, w, C, xsh, act):
     if act == 2:
         ref = F.leaky_relu(ref, 0.2)
     assert rel_err(nchw(outs[1]), ref) <= 1e-4 and rel_err(nchw(outs[0]), ref) <= 1e-4
+    assert torch.equal(outs[2], outs[1])
     assert rel_err(outs[1], outs[0]) <= 2e-5      # hi + lo carries 16 significand bits; the two epilogues contract their FMAs differently
 
 

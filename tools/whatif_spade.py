@@ -20,8 +20,10 @@ variants = {
     "tf32": (lambda wp: ops.conv_igemm(actv, wp, C, 3, 3, 1, 1, act=2, round_out=True, spade=(xs, 1, v, v, v, v)), ops.pack_weight_gb(wg, wg)),
 }
 flops = 2.0 * N * S * S * 1152 * 256
+if len(sys.argv) > 1:          # e.g. `whatif_spade.py f16`: one variant only
+    variants = {k: v for k, v in variants.items() if k in sys.argv[1:]}
 for name, (f, wp) in variants.items():
-    for dbg in (0, 1, 2, 3, 4, 8, 12, 7, 11, 15):
+    for dbg in (0, 1, 2, 3, 4, 8, 64, 12, 7, 11, 15):
         os.environ["MG_DBG"] = str(dbg)
         for _ in range(2):
             f(wp)
