@@ -288,8 +288,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
 // `stage`: this warp's 4 KB staging buffer (512 B aligned); `pending`: a TMA store of this warp may still be reading it.
 template <int SPEC>
 __device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, uint8_t* stage, const CUtensorMap* tmHi, const CUtensorMap* tmLo,
-                                                        uint64_t* tfull, uint32_t parity, uint32_t t_acc, int nt, int tw, int th, int tn,
-                                                        int quarter, int half, int lane, bool& pending, long long* w_tfull) {
+                                                        uint64_t* tfull, uint64_t* tempty, uint32_t parity, uint32_t t_acc, int nt, int tw,
+                                                        int th, int tn, int quarter, int half, int lane, bool& pending, long long* w_tfull) {
     constexpr int act = SPEC == 1 ? 2 : 0;
     const int ch_tile = p.BN >> 1;                      // 128
     const int ow = tw * 16 + (lane & 15), oh = th * 8 + quarter * 2 + (lane >> 4);
@@ -310,6 +310,7 @@ __device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, ui
     if (w_tfull) *w_tfull += clock64() - t0;
     tc_fence_after();
     const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
+    bool released = false;
 #pragma unroll 1
     for (int g = 0; g < 2; ++g) {
         if (MG_DBGV(p) & 4) break;
@@ -325,6 +326,13 @@ __device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, ui
         for (int i = 0; i < 8; ++i) xv[i] = xok ? __ldg(reinterpret_cast<const float4*>(xrow + cch + 4 * i)) : zero4;
         if (p.epi_xpf && xok && g == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(xg0 + 32));
         tmem_ld_wait();
+        if (g == 1) {
+            // the last accumulator columns of this warp are in registers: hand the TMEM buffer back to the MMA issuer NOW, not
+            // after the second group's arithmetic and stores (role profile: the issuer spent 32 % of the kernel waiting for it)
+            tc_fence_before();
+            mbar_arrive(tempty);
+            released = true;
+        }
         if (pending) { if (lane == 0) tma_store_wait_read(); __syncwarp(); pending = false; }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                    // 16-byte chunk = 8 channels
@@ -369,6 +377,7 @@ __device__ __forceinline__ void epilogue_tile_spade_tma(const IgemmParams& p, ui
         }
         pending = true;
     }
+    if (!released) { tc_fence_before(); mbar_arrive(tempty); }
 }
 
 }  // namespace mg

@@ -372,10 +372,9 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tw = m % p.tiles_w;
                 const int th = (m / p.tiles_w) % p.tiles_h;
                 const int tn = m / m_tiles_per_img;
-                epilogue_tile_spade_tma<SPEC>(p, stage, &tmOHi, &tmOLo, &tfull_bar[acc], aph, tmem_base + (uint32_t)(acc * p.acc_cols), nt, tw,
-                                              th, tn, quarter, half, lane, pending, prof ? &w_tfull : nullptr);
-                tc_fence_before();
-                mbar_arrive(&tempty_bar[acc]);
+                epilogue_tile_spade_tma<SPEC>(p, stage, &tmOHi, &tmOLo, &tfull_bar[acc], &tempty_bar[acc], aph,
+                                              tmem_base + (uint32_t)(acc * p.acc_cols), nt, tw, th, tn, quarter, half, lane, pending,
+                                              prof ? &w_tfull : nullptr);      // releases the accumulator itself
                 ++ntile;
                 if (++acc == 2) { acc = 0; aph ^= 1; }
             }
