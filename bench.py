@@ -624,7 +624,7 @@ def run_native(a):
                 "ms_per_launch": kms, "flops_per_launch": kflops}
             wtf, wms, wflops, wkind = worst_kernel_roofline(a.batch)
             line["roofline_worst"] = {
-                "kernel": "igemm_tf32_kernel<0,16> (generic implicit-GEMM conv, up_3.conv_0 shape 3x3 128->64 at 512x512, %s)" % wkind,
+                "kernel": "conv3x3_group_kernel<0,16> (3x3 implicit-GEMM conv on the halo-patch + M-tile-group schedule, up_3.conv_0 shape 128->64 at 512x512, %s)" % wkind,
                 "bound": "tensor", "achieved": wtf, "peak": peak_tf, "unit": "TFLOP/s", "frac": wtf / peak_tf, "traffic": None,
                 "note": "algorithmic FLOPs (one product per MAC); the split-precision form issues 3 products per MAC",
                 "ms_per_launch": wms, "flops_per_launch": wflops}
