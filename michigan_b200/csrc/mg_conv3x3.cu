@@ -192,9 +192,11 @@ conv3x3_group_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int mt = 0; mt < kGM; ++mt) {
                 const int acc = buf * kGM + mt;
                 epilogue_tile<SPEC, CW>(p, scr, &tfull[acc], tph, tmem_base + (uint32_t)(acc * p.acc_cols), nt, gw * kGM + mt, th, tn,
-                                        quarter, half, lane, nullptr);
-                tc_fence_before();
-                mbar_arrive(&tempty[acc]);
+                                        quarter, half, lane, nullptr, p.epi_early ? &tempty[acc] : nullptr);
+                if (!p.epi_early) {
+                    tc_fence_before();
+                    mbar_arrive(&tempty[acc]);
+                }
             }
             if (++buf == q.nbuf) { buf = 0; tph ^= 1; }
         }

@@ -48,6 +48,7 @@ struct IgemmParams {
     const float* gbias1;
     const float* bbias;
     float* aux;   // SPADE: optional [N,OH,OW,Cout] copy of (1 + gamma) for the backward pass
+    int epi_early;                     // transposed epilogue releases the accumulator after its last TMEM read (MG_EPI_EARLY)
     int epi_xpf;                       // TMA SPADE epilogue: prefetch x ahead of the accumulator wait (MG_EPI_TMA=2)
     int epi_impl, epi_cw16, epi_off;   // 1 = transposed/coalesced epilogue (default), 2 = SPADE row-per-lane + TMA stores; scratch offset in smem
     // halo mode (3x3, stride 1, pad 1): one [PW x (TH+2)] input patch per K chunk serves all 9 taps
@@ -80,7 +81,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // CW: channels per epilogue chunk (16 or 32), compile time so that the per-chunk register arrays are sized exactly.
 template <int SPEC, int CW>
 __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, uint64_t* tfull, uint32_t parity, uint32_t t_acc,
-                                              int nt, int tw, int th, int tn, int quarter, int half, int lane, long long* w_tfull) {
+                                              int nt, int tw, int th, int tn, int quarter, int half, int lane, long long* w_tfull,
+                                              uint64_t* tempty = nullptr) {
+    // tempty != nullptr (IgemmParams::epi_early): this function releases the accumulator itself, right after the last TMEM
+    // read of the tile's last chunk instead of after its arithmetic and stores; the caller then must not arrive again.
     constexpr bool kS = SPEC == 1 || SPEC == 2;
     const bool spade = kS ? true : (p.epi == 1);
     const int act = SPEC == 1 ? 2 : (SPEC == 2 ? 0 : p.act);
@@ -118,8 +122,13 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
     if (w_tfull) *w_tfull += clock64() - t0;
     tc_fence_after();
     const uint32_t t_row = t_acc + ((uint32_t)(quarter * 32) << 16);
+    bool released = tempty == nullptr;
     for (int cb = 0; cb < span; cb += cw) {
         if (MG_DBGV(p) & 4) break;
+        const bool last_chunk = cb + cw >= span;
+        auto release = [&]() {
+            if (last_chunk && !released) { tc_fence_before(); mbar_arrive(tempty); released = true; }
+        };
         const int col = half * span + cb;          // first column of this chunk (gamma part for SPADE)
         float4 av[passes], bv[passes], pre[passes];
         const int cch = (spade ? nt * ch_tile : nt * p.BN) + col + q * 4;
@@ -163,6 +172,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
             if (cw == 32) tmem_ld16(t_row + (uint32_t)(col + ch_tile + 16), b1);
         }
         tmem_ld_wait();
+        if (!p.merged) release();
         const bool ch_ok = cch < p.Cout;
         transpose(g0, g1, av, false);
         // Per-pixel side loads (SPADE: the tensor being normalised; else the residual): issued as soon as the first
@@ -173,7 +183,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
             for (int j = 0; j < passes; ++j)
                 if ((vmask >> j) & 1u) pre[j] = __ldg(reinterpret_cast<const float4*>(side + (size_t)srco[j] * p.Cout + cch));
         }
-        if (p.merged) load_chunk(col + p.BN, av, true);   // split precision, merged N: + A_hi * W_lo columns
+        if (p.merged) { load_chunk(col + p.BN, av, true); if (!spade) release(); }   // split precision, merged N: + A_hi * W_lo columns
         if (spade) transpose(b0, b1, bv, false);
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = bias4, sh4 = bias4, g14 = bias4, bb4 = bias4;
         if (ch_ok) {
@@ -198,7 +208,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
                 av[j] = make_float4(fmaf(xv.x, sc4.x, sh4.x) * gs.x, fmaf(xv.y, sc4.y, sh4.y) * gs.y,
                                     fmaf(xv.z, sc4.z, sh4.z) * gs.z, fmaf(xv.w, sc4.w, sh4.w) * gs.w);
             }
-            if (p.merged) load_chunk(col + ch_tile + p.BN, bv, true);
+            if (p.merged) { load_chunk(col + ch_tile + p.BN, bv, true); release(); }
         }
         if (!ch_ok) continue;
 #pragma unroll
@@ -275,6 +285,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
             }
         }
     }
+    if (!released) { tc_fence_before(); mbar_arrive(tempty); }
 }
 
 // SPADE -> bf16 hi/lo operand, row-per-lane + TMA stores (IgemmParams::epi_impl == 2; SPEC 1 LeakyReLU, SPEC 2 no activation).

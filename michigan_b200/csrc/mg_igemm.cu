@@ -341,9 +341,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int th = (m / p.tiles_w) % p.tiles_h;
             const int tn = m / m_tiles_per_img;
             epilogue_tile<SPEC, CW>(p, scr, &tfull_bar[acc], aph, tmem_base + (uint32_t)(acc * p.acc_cols), nt, tw, th, tn, quarter, half,
-                                    lane, prof ? &w_tfull : nullptr);
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+                                    lane, prof ? &w_tfull : nullptr, p.epi_early ? &tempty_bar[acc] : nullptr);
+            if (!p.epi_early) {
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+            }
             ++ntile;
             if (++acc == 2) { acc = 0; aph ^= 1; }
         }
@@ -596,7 +598,7 @@ int igemm_launch(const mg_igemm_args* a, cudaStream_t stream) {
     const int epi_impl_env = a->epi == MG_EPI_SPADE ? tune(TK_EPI_IMPL_SPADE) : tune(TK_EPI_IMPL);
     // epilogue chunk width: 16 channels (no register spills) unless MG_EPI_CW16=0 / MG_EPI_CW_SPADE=32 ask for 32
     const int epi_cw16_env = tune(TK_EPI_CW16);
-    p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env;
+    p.epi_impl = epi_impl_env; p.epi_cw16 = epi_cw16_env; p.epi_early = tune(TK_EPI_EARLY) ? 1 : 0;
     // epilogue chunk width (channels per TMEM->scratch->register round): 16 everywhere by default (no register spills,
     // 20 KB of scratch => one more pipeline stage at BN = 256); MG_EPI_CW16=0 / MG_EPI_CW_SPADE=32 select 32 where possible.
     const int span_epi = a->epi == MG_EPI_SPADE ? (BN >> 2) : (BN >> 1);

@@ -34,6 +34,7 @@ enum TuneKnob {
     TK_WGRAD_HALO,       // MG_WGRAD_HALO: bf16 stride-1 weight gradients load one input patch per stage for all KW taps (default 1)
     TK_EPI_TMA,          // MG_EPI_TMA: SPADE -> bf16 hi/lo epilogue at BN 256 row-per-lane through smem staging + TMA stores (default 1)
     TK_BN_FILL,          // MG_BN_FILL: generic convs whose tiles do not fill the SMs use a narrower BN (default 1)
+    TK_EPI_EARLY,        // MG_EPI_EARLY: transposed epilogue hands the accumulator back after its last TMEM read (default 0: not yet measured)
     TK_COUNT
 };
 int tune(int knob);
