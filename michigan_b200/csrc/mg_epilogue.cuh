@@ -288,7 +288,10 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* scr, 
     if (!released) { tc_fence_before(); mbar_arrive(tempty); }
 }
 
-// SPADE -> bf16 hi/lo operand, row-per-lane + TMA stores (IgemmParams::epi_impl == 2; SPEC 1 LeakyReLU, SPEC 2 no activation).
+// SPADE -> bf16 hi/lo operand, row-per-lane + TMA stores (IgemmParams::epi_impl == 2; SPEC 1 LeakyReLU, SPEC 2 no activation):
+//     out = act( norm(x) * (1 + gamma) + beta ),  gamma | beta = this tile's accumulator halves
+// (reference: normalization.py:110-116 with the batch-norm folded into nscale/nshift, LeakyReLU 0.2 of architecture.py:85 for
+// norm_0 / norm_1, none for norm_s; x is read at half resolution when the block's 2x nearest upsample is folded, generator.py:72).
 // Preconditions (checked by the launcher): BN = 256 (gamma | beta halves of 128 columns, this warp owns 64 output channels),
 // tile 16 x 8 pixels of ONE image, plain output layout, no merged split.  The lane keeps its TMEM row = pixel; the 16-bit
 // results of a 32-channel group are laid down as [32 pixels][64 B] in the SWIZZLE_64B pattern (16-byte chunk c of row r at
