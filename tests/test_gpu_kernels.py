@@ -474,6 +474,20 @@ def test_spade_epilogue_tma_store(gen, N, h, w, C, xsh, act):
     assert rel_err(outs[1], outs[0]) <= 2e-5      # hi + lo carries 16 significand bits; the two epilogues contract their FMAs differently
 
 
+@pytest.mark.parametrize("N,H,W,Cin", [(2, 32, 64, 64), (1, 20, 45, 64), (1, 9, 33, 32)])
+def test_conv_img_forward(gen, N, H, W, Cin):
+    """conv_img (generator.py:222-224: tanh(conv3x3(leaky_relu(x, 0.2)), Cin -> 3, NCHW output) vs torch, fp32 both sides: 1e-5 of
+    the output range; ragged tiles (the kernel works on 8 x 32 pixel tiles with a one-pixel halo)."""
+    ops = _ops()
+    x = torch.randn(N, Cin, H, W, generator=gen).to(dev)
+    w = (torch.randn(3, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5).to(dev)
+    b = torch.randn(3, generator=gen).to(dev) * 0.1
+    ref = torch.tanh(F.conv2d(F.leaky_relu(x, 0.2), w, b, padding=1))
+    got = ops.conv_img(nhwc(x), w, b)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 1e-5
+
+
 def test_input_prologue_kernels_vs_reference_formulas(gen):
     """The GPU input prologue (noise pyramid, orientation RGB, hole mask) against numpy/cv2 restatements of the reference's
     per-sample CPU functions (data/base_dataset.py:335-396) on identical random draws."""
