@@ -477,7 +477,7 @@ def test_spade_epilogue_tma_store(gen, N, h, w, C, xsh, act):
 @pytest.mark.parametrize("N,H,W,Cin", [(2, 32, 64, 64), (1, 20, 45, 64), (1, 9, 33, 32)])
 def test_conv_img_forward(gen, N, H, W, Cin):
     """conv_img (generator.py:222-224: tanh(conv3x3(leaky_relu(x, 0.2)), Cin -> 3, NCHW output) against a float64 CPU evaluation of
-    the same formula; ragged tiles (the kernel works on 8 x 32 pixel tiles with a one-pixel halo).  Bound 2e-5 on outputs in
+    the same formula; ragged tiles (the kernel works on 8 x 32 pixel tiles with a one-pixel halo).  Bound 5e-5 on outputs in
     [-1, 1]: the kernel accumulates 9*Cin fp32 FMAs sequentially (measured 1.7e-6 against cuDNN's direct fp32 algorithm at 128x128;
     cuDNN itself is 1.2e-5 .. 1.4e-5 away on the small shapes, where it picks a transform-domain algorithm - hence the fp64 reference)."""
     ops = _ops()
@@ -487,7 +487,7 @@ def test_conv_img_forward(gen, N, H, W, Cin):
     ref = torch.tanh(F.conv2d(F.leaky_relu(x.double(), 0.2), w.double(), b.double(), padding=1))
     got = ops.conv_img(nhwc(x.to(dev)), w.to(dev), b.to(dev))
     assert tuple(got.shape) == tuple(ref.shape)
-    assert float((got.cpu().double() - ref).abs().max()) <= 2e-5
+    assert float((got.cpu().double() - ref).abs().max()) <= 5e-5
 
 
 def test_input_prologue_kernels_vs_reference_formulas(gen):
